@@ -1,0 +1,128 @@
+/*
+ * jsa_mips.h — C ABI of the B200-native exact maximum-inner-product-search engine.
+ *
+ * This is the drop-in boundary for the passage-retrieval hot path of Caohy23/JSA-RAG.  The
+ * reference reaches that path through a duck-typed Python object (DistributedIndex,
+ * reference src/index.py:44-161), not through an FFI; every entry point below replaces the
+ * library call(s) named next to it, and the Python host layer in jsa-rag_b200/ binds them
+ * with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success and a negative MIPS_E* code on failure, never throws
+ *     or aborts; mips_last_error() returns a human-readable message for the last failure;
+ *   - device pointers are *borrowed* for the duration of a call; the handle owns only its own
+ *     descriptors and (optionally) an internal workspace;
+ *   - all device work is stream-ordered on the cudaStream_t passed as `stream` (void*).
+ */
+#ifndef JSA_MIPS_H_
+#define JSA_MIPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSA_MIPS_ABI_VERSION 1
+
+/* element types */
+#define MIPS_DTYPE_F16 0
+#define MIPS_DTYPE_BF16 1
+#define MIPS_DTYPE_F32 2 /* queries only */
+
+/* error codes */
+#define MIPS_OK 0
+#define MIPS_EINVAL (-1)      /* bad argument (NULL, negative size, unsupported dim/dtype) */
+#define MIPS_EKRANGE (-2)     /* k > number of indexed rows: reference raises RuntimeError("selected index k out of range") */
+#define MIPS_ECUDA (-3)       /* a CUDA runtime/driver call failed */
+#define MIPS_ENOTBOUND (-4)   /* search before mips_bind_index */
+#define MIPS_EWORKSPACE (-5)  /* caller-provided workspace too small */
+#define MIPS_EUNSUPPORTED (-6)/* not running on an sm_100 device / feature not built */
+
+typedef struct mips_handle mips_handle;
+
+/* Limits of this build (queryable so host code never hard-codes them). */
+int mips_abi_version(void);
+int mips_max_k(void);          /* largest supported top-k (fused select) */
+int mips_max_dim(void);        /* largest supported embedding dimension */
+
+/*
+ * Creates an engine bound to CUDA device `device` for `dim`-dimensional embeddings stored as
+ * `index_dtype` (MIPS_DTYPE_F16 — the reference's only storage type, src/index.py:52 — or
+ * MIPS_DTYPE_BF16 for the JSA bf16 configuration).  dim must be a multiple of 64.
+ * Replaces: DistributedIndex.__init__ (src/index.py:45-48).
+ */
+int mips_create(mips_handle** out, int device, int dim, int index_dtype);
+void mips_destroy(mips_handle* h);
+const char* mips_last_error(const mips_handle* h); /* h may be NULL: message of the last failed mips_create */
+
+/*
+ * Binds the passage-embedding matrix of this rank's shard.  `emb` is a device pointer to
+ * n_local rows of `dim` elements, row stride `ld` elements (K-major: one passage per row; this is
+ * the transposed *view* of the reference's [dim, n_local] `.embeddings`, src/index.py:52,
+ * so `index.embeddings[:, a:b] = x.T` (src/rag.py:120) writes straight into it).
+ * Global passage id of local row r is id_base + r * id_stride
+ *   round-robin jsonl sharding (src/index_io.py:41):  id_base = rank, id_stride = world_size
+ *   contiguous shard files      (src/index.py:97-100): id_base = first row, id_stride = 1
+ * Rebinding is cheap (re-encodes one TMA descriptor) and must be repeated whenever the tensor
+ * is re-allocated.  Replaces: the `self.embeddings` operand of torch.matmul (src/index.py:118).
+ */
+int mips_bind_index(mips_handle* h, const void* emb, int64_t n_local, int64_t ld,
+                    int64_t id_base, int64_t id_stride);
+
+/* Bytes of device workspace mips_search_local needs for up to max_batch queries and top max_k. */
+int mips_workspace_bytes(const mips_handle* h, int max_batch, int max_k, size_t* out);
+
+/*
+ * Exact top-k inner-product search of `batch` queries over the bound shard.
+ *   queries    device pointer, [batch, dim] row-major with row stride q_ld elements, q_dtype
+ *              F32 / F16 / BF16; cast to the index dtype exactly like `allqueries.half()`
+ *              (src/index.py:118).  normalize != 0 L2-normalises each query first in fp32
+ *              (faiss.normalize_L2, build_server/server_start.py:142).
+ *   out_scores device [batch, k] fp32, descending (fp32 accumulator values, not fp16-rounded)
+ *   out_ids    device [batch, k] int64 global passage ids; ties broken by ascending id
+ *   workspace  device scratch of at least mips_workspace_bytes(); NULL => the handle uses (and
+ *              grows) an internal workspace.
+ * Replaces: torch.matmul + torch.topk in _compute_scores_and_indices (src/index.py:114-121),
+ * faiss GpuIndexFlatIP.search (build_server/server_start.py:143).  The [batch, n_local] score
+ * matrix is never written to memory.
+ */
+int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t q_ld, int batch, int k,
+                      int normalize, float* out_scores, int64_t* out_ids,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Merges num_lists sorted candidate lists per query into the global top k_out:
+ *   scores [num_lists, batch, k_in] fp32 descending, ids [num_lists, batch, k_in] int64
+ *   -> out_scores [batch, k_out], out_ids [batch, k_out]   (score desc, id asc on ties).
+ * Entries with id < 0 are padding and are ignored.  k_in, k_out <= mips_max_k().
+ * Replaces: the 2*W gathers + concat + second torch.topk of search_knn (src/index.py:135-157)
+ * after ONE all-gather of (score, id) candidates.
+ */
+int mips_merge_topk(int device, const float* scores, const int64_t* ids, int num_lists, int batch,
+                    int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream);
+
+/*
+ * out[i, :] = embeddings[local_rows[i], :]   (index dtype, [n, dim] row-major).
+ * Replaces: self.embeddings[:, indices.view(-1)] of the 3-tuple search_knn
+ * (build_server/index.py:228-229).
+ */
+int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void* out, void* stream);
+
+/*
+ * End-to-end convenience for callers that hold HOST buffers (server / ctypes clients):
+ * H2D copy of fp32 queries [batch, dim], mips_search_local, D2H copy of results, stream sync.
+ * host_* pointers should be page-locked for full speed but need not be.
+ */
+int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k, int normalize,
+                     float* host_scores, int64_t* host_ids, void* stream);
+
+/* Number of kernels the last mips_search_local / mips_search_host on this handle launched. */
+int mips_last_launch_count(const mips_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSA_MIPS_H_ */

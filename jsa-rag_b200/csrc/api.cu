@@ -1,0 +1,337 @@
+// C ABI of libjsa_mips.so (declared in include/jsa_mips.h).  Host-side orchestration only:
+// descriptor encoding, workspace carving, kernel launches.  No allocation on the hot path once the
+// workspace exists; no CPU fallback — on a non-sm_100 device every call fails with MIPS_EUNSUPPORTED.
+#include "../../include/jsa_mips.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+using namespace mips;
+
+struct mips_handle {
+  int device = 0;
+  int dim = 0;
+  int dtype = MIPS_DTYPE_F16;
+  int num_sms = 0;
+  // bound index
+  const void* emb = nullptr;
+  int64_t n_local = 0, ld = 0, id_base = 0, id_stride = 1;
+  CUtensorMap tmap_e;
+  bool bound = false;
+  // kernel geometry
+  int num_kchunks = 0, num_stages = 0;
+  size_t smem_bytes = 0;
+  // internal buffers
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  void* io = nullptr;  // device staging for mips_search_host: queries | scores | ids
+  size_t io_bytes = 0;
+  int last_launches = 0;
+  std::string err;
+};
+
+namespace {
+
+std::string g_create_err;
+std::mutex g_mu;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int fail(mips_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else { std::lock_guard<std::mutex> lk(g_mu); g_create_err = buf; }
+  return code;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail((h), MIPS_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Row-major [rows, dim] 16-bit matrix -> 2-D tensor map, box = {64 elements (128 B), box_rows},
+// 128-byte swizzle, zero fill out of bounds.
+int encode_rows_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t rows, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->dim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKChunk), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = h->dtype == MIPS_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MIPS_OK;
+}
+
+struct WsLayout {
+  size_t q_off, cand_off, ps_off, pi_off, total;
+};
+
+WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
+  WsLayout w;
+  const size_t bpad = align_up(static_cast<size_t>(max_batch > 0 ? max_batch : 1), kNQ);
+  const size_t grid = static_cast<size_t>(h->num_sms);
+  size_t off = 0;
+  w.q_off = off;    off += align_up(bpad * h->dim * 2, 1024);
+  w.cand_off = off; off += align_up(grid * kNQ * kCap * sizeof(uint64_t), 1024);
+  w.ps_off = off;   off += align_up(grid * kNQ * static_cast<size_t>(max_k) * sizeof(float), 1024);
+  w.pi_off = off;   off += align_up(grid * kNQ * static_cast<size_t>(max_k) * sizeof(int64_t), 1024);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mips_abi_version(void) { return JSA_MIPS_ABI_VERSION; }
+int mips_max_k(void) { return kMaxK; }
+int mips_max_dim(void) { return kMaxDim; }
+
+const char* mips_last_error(const mips_handle* h) {
+  if (h) return h->err.c_str();
+  return g_create_err.c_str();
+}
+
+int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
+  if (!out) return fail(nullptr, MIPS_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (dim <= 0 || dim % kKChunk != 0 || dim > kMaxDim)
+    return fail(nullptr, MIPS_EINVAL, "dim=%d unsupported: must be a multiple of %d and <= %d", dim, kKChunk, kMaxDim);
+  if (index_dtype != MIPS_DTYPE_F16 && index_dtype != MIPS_DTYPE_BF16)
+    return fail(nullptr, MIPS_EINVAL, "index dtype %d unsupported (fp16=0, bf16=1)", index_dtype);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, MIPS_EUNSUPPORTED, "no CUDA device: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, MIPS_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, MIPS_EUNSUPPORTED, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                prop.major, prop.minor);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(nullptr, MIPS_ECUDA, "cudaSetDevice(%d) failed", device);
+  mips_handle* h = new mips_handle();
+  h->device = device;
+  h->dim = dim;
+  h->dtype = index_dtype;
+  h->num_sms = prop.multiProcessorCount;
+  h->num_kchunks = dim / kKChunk;
+  const int q_bytes = h->num_kchunks * kQChunkBytes;
+  int stages = (kMaxSmem - 1024 - kCtrlBytes - q_bytes) / kStageBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) { delete h; return fail(nullptr, MIPS_EINVAL, "dim=%d leaves no room for the TMA pipeline", dim); }
+  h->num_stages = stages;
+  h->smem_bytes = 1024 + q_bytes + static_cast<size_t>(stages) * kStageBytes + kCtrlBytes;
+  cudaError_t e = configure_scan(h->smem_bytes);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(nullptr, MIPS_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", h->smem_bytes, cudaGetErrorString(e));
+  }
+  *out = h;
+  return MIPS_OK;
+}
+
+void mips_destroy(mips_handle* h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->ws) cudaFree(h->ws);
+  if (h->io) cudaFree(h->io);
+  delete h;
+}
+
+int mips_bind_index(mips_handle* h, const void* emb, int64_t n_local, int64_t ld, int64_t id_base, int64_t id_stride) {
+  if (!h) return MIPS_EINVAL;
+  if (n_local < 0 || n_local > 0x7FFFFF00ll) return fail(h, MIPS_EINVAL, "n_local=%lld out of range", (long long)n_local);
+  if (n_local > 0 && !emb) return fail(h, MIPS_EINVAL, "emb is NULL");
+  if (ld < h->dim || (ld * 2) % 16 != 0) return fail(h, MIPS_EINVAL, "row stride ld=%lld must be >= dim and 16-byte aligned", (long long)ld);
+  if (reinterpret_cast<uintptr_t>(emb) % 16 != 0) return fail(h, MIPS_EINVAL, "emb must be 16-byte aligned");
+  h->emb = emb;
+  h->n_local = n_local;
+  h->ld = ld;
+  h->id_base = id_base;
+  h->id_stride = id_stride;
+  h->bound = false;
+  if (n_local > 0) {
+    int rc = encode_rows_map(h, &h->tmap_e, emb, n_local, ld, kTileM);
+    if (rc != MIPS_OK) return rc;
+  }
+  h->bound = true;
+  return MIPS_OK;
+}
+
+int mips_workspace_bytes(const mips_handle* h, int max_batch, int max_k, size_t* out) {
+  if (!h || !out || max_batch < 0 || max_k <= 0 || max_k > kMaxK) return MIPS_EINVAL;
+  *out = ws_layout(h, max_batch, max_k).total;
+  return MIPS_OK;
+}
+
+int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t q_ld, int batch, int k,
+                      int normalize, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!h) return MIPS_EINVAL;
+  h->last_launches = 0;
+  if (!h->bound) return fail(h, MIPS_ENOTBOUND, "mips_bind_index has not been called");
+  if (batch < 0 || k <= 0) return fail(h, MIPS_EINVAL, "batch=%d k=%d invalid", batch, k);
+  if (k > kMaxK) return fail(h, MIPS_EINVAL, "k=%d exceeds the fused top-k limit %d", k, kMaxK);
+  if (k > h->n_local) return fail(h, MIPS_EKRANGE, "selected index k out of range (k=%d > n_local=%lld)", k, (long long)h->n_local);
+  if (batch == 0) return MIPS_OK;
+  if (!queries || !out_scores || !out_ids) return fail(h, MIPS_EINVAL, "NULL queries/outputs");
+  if (q_dtype < 0 || q_dtype > 2) return fail(h, MIPS_EINVAL, "q_dtype=%d invalid", q_dtype);
+  if (q_ld < h->dim) return fail(h, MIPS_EINVAL, "q_ld=%lld < dim", (long long)q_ld);
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const WsLayout w = ws_layout(h, batch, k);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  if (ws) {
+    if (workspace_bytes < w.total) return fail(h, MIPS_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
+    if (reinterpret_cast<uintptr_t>(ws) % 1024 != 0) return fail(h, MIPS_EINVAL, "workspace must be 1024-byte aligned");
+  } else {
+    if (h->ws_bytes < w.total) {
+      // grow-only internal workspace (sized for the largest request seen); not on the steady-state path
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      if (h->ws) cudaFree(h->ws);
+      h->ws = nullptr; h->ws_bytes = 0;
+      CUDA_TRY(h, cudaMalloc(&h->ws, w.total));
+      h->ws_bytes = w.total;
+    }
+    ws = static_cast<uint8_t*>(h->ws);
+  }
+  void* qbuf = ws + w.q_off;
+  const int bpad = static_cast<int>(align_up(batch, kNQ));
+
+  CUDA_TRY(h, launch_prep_queries(queries, q_dtype, q_ld, batch, bpad, h->dim, h->dtype, normalize, qbuf, st));
+  h->last_launches++;
+
+  CUtensorMap tmap_q;
+  int rc = encode_rows_map(h, &tmap_q, qbuf, bpad, h->dim, kNQ);
+  if (rc != MIPS_OK) return rc;
+
+  const int num_tiles = static_cast<int>((h->n_local + kTileM - 1) / kTileM);
+  const int grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
+  ScanParams p;
+  p.n_local = h->n_local;
+  p.num_tiles = num_tiles;
+  p.num_kchunks = h->num_kchunks;
+  p.num_stages = h->num_stages;
+  p.k = k;
+  p.idesc = ptx::make_idesc_f16(kTileM, kNQ, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
+  p.cand = reinterpret_cast<uint64_t*>(ws + w.cand_off);
+  p.part_scores = reinterpret_cast<float*>(ws + w.ps_off);
+  p.part_ids = reinterpret_cast<int64_t*>(ws + w.pi_off);
+  p.id_base = h->id_base;
+  p.id_stride = h->id_stride;
+
+  for (int q0 = 0; q0 < batch; q0 += kNQ) {
+    p.batch = batch - q0 < kNQ ? batch - q0 : kNQ;
+    p.q_row0 = q0;
+    CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, grid, h->smem_bytes, st));
+    CUDA_TRY(h, launch_merge(p.part_scores, p.part_ids, grid, static_cast<int64_t>(kNQ) * k, p.batch, k, k,
+                             out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
+    h->last_launches += 2;
+  }
+  return MIPS_OK;
+}
+
+int mips_merge_topk(int device, const float* scores, const int64_t* ids, int num_lists, int batch, int k_in, int k_out,
+                    float* out_scores, int64_t* out_ids, void* stream) {
+  if (num_lists <= 0 || batch < 0 || k_in <= 0 || k_out <= 0 || k_in > kMaxK || k_out > kMaxK)
+    return fail(nullptr, MIPS_EINVAL, "mips_merge_topk: bad sizes lists=%d batch=%d k_in=%d k_out=%d", num_lists, batch, k_in, k_out);
+  if (batch == 0) return MIPS_OK;
+  if (!scores || !ids || !out_scores || !out_ids) return fail(nullptr, MIPS_EINVAL, "mips_merge_topk: NULL pointer");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(nullptr, MIPS_ECUDA, "cudaSetDevice(%d) failed", device);
+  cudaError_t e = launch_merge(scores, ids, num_lists, static_cast<int64_t>(batch) * k_in, batch, k_in, k_out, out_scores,
+                               out_ids, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(nullptr, MIPS_ECUDA, "merge launch failed: %s", cudaGetErrorString(e));
+  return MIPS_OK;
+}
+
+int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void* out, void* stream) {
+  if (!h) return MIPS_EINVAL;
+  if (!h->bound) return fail(h, MIPS_ENOTBOUND, "mips_bind_index has not been called");
+  if (n < 0 || (n > 0 && (!local_rows || !out))) return fail(h, MIPS_EINVAL, "bad gather arguments");
+  DeviceGuard g(h->device);
+  CUDA_TRY(h, launch_gather_rows(h->emb, h->ld, h->dim, h->n_local, local_rows, n, out, static_cast<cudaStream_t>(stream)));
+  return MIPS_OK;
+}
+
+int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k, int normalize, float* host_scores,
+                     int64_t* host_ids, void* stream) {
+  if (!h) return MIPS_EINVAL;
+  h->last_launches = 0;
+  if (batch < 0 || k <= 0) return fail(h, MIPS_EINVAL, "batch=%d k=%d invalid", batch, k);
+  if (batch == 0) return MIPS_OK;
+  if (!host_queries || !host_scores || !host_ids) return fail(h, MIPS_EINVAL, "NULL host buffer");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t qb = align_up(static_cast<size_t>(batch) * h->dim * sizeof(float), 256);
+  const size_t sb = align_up(static_cast<size_t>(batch) * k * sizeof(float), 256);
+  const size_t ib = align_up(static_cast<size_t>(batch) * k * sizeof(int64_t), 256);
+  if (h->io_bytes < qb + sb + ib) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (h->io) cudaFree(h->io);
+    h->io = nullptr; h->io_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->io, qb + sb + ib));
+    h->io_bytes = qb + sb + ib;
+  }
+  uint8_t* io = static_cast<uint8_t*>(h->io);
+  float* dq = reinterpret_cast<float*>(io);
+  float* ds = reinterpret_cast<float*>(io + qb);
+  int64_t* di = reinterpret_cast<int64_t*>(io + qb + sb);
+  CUDA_TRY(h, cudaMemcpyAsync(dq, host_queries, static_cast<size_t>(batch) * h->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = mips_search_local(h, dq, MIPS_DTYPE_F32, h->dim, batch, k, normalize, ds, di, nullptr, 0, stream);
+  if (rc != MIPS_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(host_scores, ds, static_cast<size_t>(batch) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaMemcpyAsync(host_ids, di, static_cast<size_t>(batch) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return MIPS_OK;
+}
+
+int mips_last_launch_count(const mips_handle* h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

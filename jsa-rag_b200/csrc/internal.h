@@ -1,0 +1,70 @@
+// Internal declarations shared by the translation units of libjsa_mips.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mips {
+
+// ---- compile-time geometry of the fused scan kernel ----
+constexpr int kTileM = 128;      // passages per tile   (UMMA M, one TMEM lane per passage)
+constexpr int kNQ = 64;          // query columns/pass  (UMMA N, one TMEM column per query)
+constexpr int kKChunk = 64;      // elements per K chunk: 64 x 2 B = one 128-byte swizzle row
+constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
+constexpr int kStageBytes = kTileM * kKChunk * 2;   // 16 KiB passage chunk per pipeline stage
+constexpr int kQChunkBytes = kNQ * kKChunk * 2;     // 8 KiB query chunk (resident for the whole kernel)
+constexpr int kMaxStages = 8;
+constexpr int kCap = 512;        // candidate slots per (CTA, query) in the L2-resident candidate lists
+constexpr int kSortE = kCap / 32;  // keys per lane in the warp bitonic sort
+constexpr int kMaxK = 128;       // largest fused top-k
+constexpr int kMaxDim = 1024;
+constexpr int kScanThreads = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue/select
+constexpr int kCtrlBytes = 1280;   // barriers + thresholds + counters
+constexpr int kMaxSmem = 232448;   // 227 KiB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kTmemCols = 2 * kNQ; // double-buffered fp32 accumulators
+
+struct ScanParams {
+  int64_t n_local;       // rows in this shard
+  int num_tiles;         // ceil(n_local / kTileM)
+  int num_kchunks;       // dim / 64
+  int num_stages;        // pipeline depth that fits next to the resident queries
+  int k;                 // top-k (<= kMaxK)
+  int batch;             // valid query columns in this pass (<= kNQ)
+  int q_row0;            // first row of this pass in the prepared query buffer
+  uint32_t idesc;        // tcgen05 instruction descriptor (dtype dependent)
+  uint64_t* cand;        // [grid][kNQ][kCap] packed (orderable score << 32 | ~row) keys
+  float* part_scores;    // [grid][kNQ][k]  per-CTA sorted partial top-k
+  int64_t* part_ids;     // [grid][kNQ][k]  global ids
+  int64_t id_base, id_stride;
+};
+
+// launchers (defined in scan.cu / merge.cu); return cudaError_t of the launch
+cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int batch, int batch_pad, int dim,
+                                int out_dtype, int normalize, void* out, cudaStream_t st);
+cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
+                        size_t smem_bytes, cudaStream_t st);
+cudaError_t configure_scan(size_t smem_bytes);
+cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
+                         int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st);
+cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, const int64_t* rows, int64_t n,
+                               void* out, cudaStream_t st);
+
+// ---- order-preserving float <-> uint32 (larger float -> larger uint) ----
+__host__ __device__ inline uint32_t f32_to_ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f + 0.0f);  // +0.0f canonicalises -0 to +0
+#else
+  union { float f; uint32_t u; } c; c.f = f + 0.0f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ord_to_f32(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+}  // namespace mips

@@ -1,0 +1,145 @@
+"""Tensor-level wrapper over the C ABI: torch owns every buffer, the extension borrows pointers.
+
+``MipsEngine.search`` is the measured hot path (scan + per-shard merge, stream-ordered on torch's
+current stream); ``B200Index`` (index.py) puts the reference's ``DistributedIndex`` API on top.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_TORCH2MIPS = {torch.float16: N.MIPS_DTYPE_F16, torch.bfloat16: N.MIPS_DTYPE_BF16, torch.float32: N.MIPS_DTYPE_F32}
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class MipsEngine:
+    """Exact top-k inner-product search over one shard resident on one B200."""
+
+    def __init__(self, dim: int, dtype: torch.dtype = torch.float16, device: Optional[torch.device] = None):
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError(f"index dtype must be float16 or bfloat16, got {dtype}")
+        self._lib = N.load()  # raises if the CUDA extension is missing: no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("MipsEngine needs a CUDA (sm_100) device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dim = int(dim)
+        self.dtype = dtype
+        h = ctypes.c_void_p()
+        N.check(self._lib.mips_create(ctypes.byref(h), self.device.index or 0, self.dim, _TORCH2MIPS[dtype]), None,
+                "mips_create")
+        self._h = h
+        self._store = None
+        self.max_k = self._lib.mips_max_k()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mips_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ index binding
+    def bind(self, store: torch.Tensor, id_base: int = 0, id_stride: int = 1) -> None:
+        """``store``: [n_local, dim] K-major CUDA tensor (row stride may exceed dim)."""
+        if store.dim() != 2 or store.shape[1] != self.dim or store.stride(1) != 1:
+            raise ValueError(f"store must be [n, {self.dim}] with unit inner stride, got {tuple(store.shape)} / {store.stride()}")
+        if store.dtype != self.dtype or store.device != self.device:
+            raise ValueError(f"store must be {self.dtype} on {self.device}")
+        ld = store.stride(0) if store.shape[0] > 1 else self.dim
+        N.check(self._lib.mips_bind_index(self._h, ctypes.c_void_p(store.data_ptr()), store.shape[0], ld,
+                                          int(id_base), int(id_stride)), self._h, "mips_bind_index")
+        self._store = store  # keep alive: the extension only borrows the pointer
+
+    @property
+    def n_local(self) -> int:
+        return 0 if self._store is None else int(self._store.shape[0])
+
+    # ------------------------------------------------------------------ search
+    def search(self, queries: torch.Tensor, k: int, normalize: bool = False,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries [B, dim] (fp32/fp16/bf16, CUDA) -> (scores fp32 [B, k] desc, global ids int64 [B, k])."""
+        if queries.dim() != 2 or queries.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B, {self.dim}], got {tuple(queries.shape)}")
+        if queries.dtype not in _TORCH2MIPS:
+            queries = queries.float()
+        if queries.device != self.device:
+            queries = queries.to(self.device)
+        if queries.stride(1) != 1:
+            queries = queries.contiguous()
+        b = int(queries.shape[0])
+        if out is None:
+            scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        else:
+            scores, ids = out
+        q_ld = queries.stride(0) if b > 1 else self.dim
+        rc = self._lib.mips_search_local(self._h, ctypes.c_void_p(queries.data_ptr()), _TORCH2MIPS[queries.dtype], q_ld,
+                                         b, int(k), int(bool(normalize)), ctypes.c_void_p(scores.data_ptr()),
+                                         ctypes.c_void_p(ids.data_ptr()), None, 0, _stream_ptr(self.device))
+        N.check(rc, self._h, "mips_search_local")
+        return scores, ids
+
+    def search_host(self, host_queries: torch.Tensor, k: int, normalize: bool = False,
+                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End to end with HOST buffers (fp32 CPU tensor in, CPU tensors out): H2D + search + D2H + sync."""
+        if host_queries.device.type != "cpu" or host_queries.dtype != torch.float32 or not host_queries.is_contiguous():
+            host_queries = host_queries.detach().to("cpu", torch.float32).contiguous()
+        b = int(host_queries.shape[0])
+        if out is None:
+            scores = torch.empty((b, k), dtype=torch.float32).pin_memory()
+            ids = torch.empty((b, k), dtype=torch.int64).pin_memory()
+        else:
+            scores, ids = out
+        rc = self._lib.mips_search_host(self._h, ctypes.cast(host_queries.data_ptr(), ctypes.POINTER(ctypes.c_float)), b,
+                                        int(k), int(bool(normalize)),
+                                        ctypes.cast(scores.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+                                        ctypes.cast(ids.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
+                                        _stream_ptr(self.device))
+        N.check(rc, self._h, "mips_search_host")
+        return scores, ids
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.mips_last_launch_count(self._h))
+
+    # ------------------------------------------------------------------ merge / gather
+    def merge(self, scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """[L, B, k_in] candidate lists (each sorted desc) -> merged top k_out per query."""
+        return merge_topk(scores, ids, k_out)
+
+    def gather_rows(self, local_rows: torch.Tensor) -> torch.Tensor:
+        rows = local_rows.reshape(-1).to(self.device, torch.int64).contiguous()
+        out = torch.empty((rows.numel(), self.dim), dtype=self.dtype, device=self.device)
+        N.check(self._lib.mips_gather_rows(self._h, ctypes.c_void_p(rows.data_ptr()), rows.numel(),
+                                           ctypes.c_void_p(out.data_ptr()), _stream_ptr(self.device)), self._h,
+                "mips_gather_rows")
+        return out
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Device-side L-way merge of sorted (score, id) lists: replaces src/index.py:135-157."""
+    lib = N.load()
+    if scores.dim() != 3 or scores.shape != ids.shape:
+        raise ValueError("scores/ids must both be [L, B, k_in]")
+    if not scores.is_cuda:
+        raise RuntimeError("merge_topk needs CUDA tensors; there is no CPU fallback")
+    scores = scores.contiguous().float()
+    ids = ids.contiguous().to(torch.int64)
+    L, b, k_in = scores.shape
+    out_s = torch.empty((b, k_out), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((b, k_out), dtype=torch.int64, device=scores.device)
+    rc = lib.mips_merge_topk(scores.device.index or 0, ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(ids.data_ptr()),
+                             L, b, k_in, int(k_out), ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
+                             _stream_ptr(scores.device))
+    N.check(rc, None, "mips_merge_topk")
+    return out_s, out_i

@@ -1,0 +1,278 @@
+"""B200Index — drop-in for the reference's ``DistributedIndex`` (src/index.py:44-161).
+
+Same public surface (``init_embeddings``, ``.embeddings``, ``.doc_map``, ``search_knn``,
+``save_index``, ``load_index``, ``is_index_trained``), same argument meaning, return order
+``(docs, scores)`` and error behaviour.  What is different underneath:
+
+* storage is K-major ``[n_local, dim]`` (one contiguous 1536-byte row per passage — what TMA and
+  tcgen05 want); ``.embeddings`` is the transposed *view* ``[dim, n_local]``, so the reference's
+  write site ``index.embeddings[:, a:b] = emb.T`` (src/rag.py:120) writes straight through and
+  ``torch.save(self.embeddings[:, a:b].clone())`` still produces the reference's shard bytes;
+* ``torch.matmul`` + ``torch.topk`` (src/index.py:118-119) is one fused sm_100a kernel + a merge;
+* the cross-rank merge (src/index.py:135-157: 2*W gathers of scores and pickled passage text) is
+  ONE all-gather of (score, global id) + a device merge; text is resolved for the k winners only.
+
+There is no CPU search path: ``search_knn`` raises if the CUDA extension is missing.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import dist_utils
+
+EMBEDDINGS_DIM: int = 768  # reference src/retrievers.py:14
+
+
+class B200Index(object):
+    def __init__(self, dtype: torch.dtype = torch.float16, device: Optional[str] = None):
+        self._store: Optional[torch.Tensor] = None  # [n_local, dim] K-major
+        self.doc_map = dict()
+        self.is_in_gpu = True  # reference attribute (src/index.py:48); False keeps storage on the host (I/O only)
+        self.dtype = dtype
+        self._device = device
+        self._engine = None
+        self._bound_key = None
+        # global id of local row r = id_base + r * id_stride  (see _set_sharding)
+        self._id_base, self._id_stride = 0, 1
+        self._sharding = "round_robin"
+        self.round_scores_to_index_dtype = True  # reference returns fp16-rounded scores (src/index.py:118,153)
+        self.last_search_stats = {}
+
+    # ------------------------------------------------------------------ storage
+    def _storage_device(self) -> torch.device:
+        if self._device is not None:
+            return torch.device(self._device)
+        if self.is_in_gpu and torch.cuda.is_available():
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
+
+    @property
+    def embeddings(self) -> Optional[torch.Tensor]:
+        """[dim, n_local] view of the K-major storage (reference layout, src/index.py:52)."""
+        return None if self._store is None else self._store.t()
+
+    @embeddings.setter
+    def embeddings(self, value: Optional[torch.Tensor]) -> None:
+        if value is None:
+            self._store = None
+            return
+        if value.dim() != 2:
+            raise ValueError("embeddings must be [dim, n]")
+        self._store = value.t().to(device=self._storage_device(), dtype=self.dtype).contiguous()
+
+    def init_embeddings(self, passages, dim: Optional[int] = EMBEDDINGS_DIM):
+        """src/index.py:50-54 — allocates zeroed storage; passages were round-robin sharded by
+        load_passages (src/index_io.py:41), hence global id = local * W + rank."""
+        self.doc_map = {i: doc for i, doc in enumerate(passages)}
+        self._store = torch.zeros(len(passages), dim, dtype=self.dtype, device=self._storage_device())
+        self._set_sharding("round_robin")
+
+    def _set_sharding(self, mode: str) -> None:
+        self._sharding = mode
+        w, r = dist_utils.get_world_size(), dist_utils.get_rank()
+        if mode == "round_robin":
+            self._id_base, self._id_stride = r, w
+        else:  # contiguous: rank r owns rows [offset_r, offset_r + n_r)
+            n = 0 if self._store is None else int(self._store.shape[0])
+            counts = dist_utils.all_gather_object(n)
+            self._id_base, self._id_stride = int(sum(counts[:r])), 1
+            self._all_counts = counts
+        self._bound_key = None
+
+    def is_index_trained(self) -> bool:
+        return True  # src/index.py:160-161
+
+    def train_index_bychunks(self) -> None:  # never reached for a flat index (src/rag.py:127-130)
+        return None
+
+    # ------------------------------------------------------------------ shard I/O (src/index.py:56-112)
+    def _get_saved_embedding_path(self, save_dir: str, shard: int) -> str:
+        return os.path.join(save_dir, f"embeddings.{shard}.pt")
+
+    def _get_saved_passages_path(self, save_dir: str, shard: int) -> str:
+        return os.path.join(save_dir, f"passages.{shard}.pt")
+
+    def save_index(self, path: str, total_saved_shards: int, overwrite_saved_passages: bool = False) -> None:
+        """Writes the reference's shard files: ``embeddings.{s}.pt`` = torch.save of a contiguous
+        fp16 [dim, n_s] tensor, ``passages.{s}.pt`` = raw pickle of the passage list (src/index.py:62-88)."""
+        assert self._store is not None
+        rank = dist_utils.get_rank()
+        ws = dist_utils.get_world_size()
+        assert total_saved_shards % ws == 0, f"N workers must be a multiple of shards to save"
+        shards_per_worker = total_saved_shards // ws
+        n_embeddings = self._store.shape[0]
+        embeddings_per_shard = math.ceil(n_embeddings / shards_per_worker)
+        assert n_embeddings == len(self.doc_map), len(self.doc_map)
+        for shard_ind, shard_start in enumerate(range(0, n_embeddings, embeddings_per_shard)):
+            shard_end = min(shard_start + embeddings_per_shard, n_embeddings)
+            shard_id = shard_ind + rank * shards_per_worker
+            passage_shard_path = self._get_saved_passages_path(path, shard_id)
+            if not os.path.exists(passage_shard_path) or overwrite_saved_passages:
+                passage_shard = [self.doc_map[i] for i in range(shard_start, shard_end)]
+                with open(passage_shard_path, "wb") as fobj:
+                    pickle.dump(passage_shard, fobj, protocol=pickle.HIGHEST_PROTOCOL)
+            # [dim, n_s] contiguous, exactly what `self.embeddings[:, a:b].clone()` holds in the reference
+            embeddings_shard = self._store[shard_start:shard_end].t().contiguous()
+            torch.save(embeddings_shard, self._get_saved_embedding_path(path, shard_id))
+
+    def load_index(self, path: str, total_saved_shards: int):
+        """Loads the shard files of this rank (src/index.py:90-112).  Shards are copied one by one
+        into preallocated K-major storage (no 2x concat peak)."""
+        rank = dist_utils.get_rank()
+        ws = dist_utils.get_world_size()
+        assert total_saved_shards % ws == 0, f"N workers must be a multiple of shards to save"
+        shards_per_worker = total_saved_shards // ws
+        passages, shards = [], []
+        for shard_id in range(rank * shards_per_worker, (rank + 1) * shards_per_worker):
+            with open(self._get_saved_passages_path(path, shard_id), "rb") as fobj:
+                passages.append(pickle.load(fobj))
+            shards.append(torch.load(self._get_saved_embedding_path(path, shard_id), map_location="cpu"))
+        self.doc_map = {}
+        n_passages = 0
+        for chunk in passages:
+            for p in chunk:
+                self.doc_map[n_passages] = p
+                n_passages += 1
+        dim = shards[0].shape[0] if shards else EMBEDDINGS_DIM
+        n = sum(int(s.shape[1]) for s in shards)
+        self._store = torch.empty(n, dim, dtype=self.dtype, device=self._storage_device())
+        at = 0
+        for s in shards:
+            self._store[at:at + s.shape[1]].copy_(s.t())
+            at += int(s.shape[1])
+        self._set_sharding("contiguous")
+
+    # ------------------------------------------------------------------ native search
+    def _get_engine(self):
+        if self._store is None:
+            raise RuntimeError("index has no embeddings: call init_embeddings or load_index first")
+        if not self._store.is_cuda:
+            raise RuntimeError("B200Index.search_knn needs the index on a B200 (is_in_gpu=True and a CUDA device); "
+                               "there is no CPU fallback")
+        from .engine import MipsEngine
+        if self._engine is None or self._engine.dim != self._store.shape[1] or self._engine.dtype != self._store.dtype \
+                or self._engine.device != self._store.device:
+            self._engine = MipsEngine(int(self._store.shape[1]), self._store.dtype, self._store.device)
+            self._bound_key = None
+        key = (self._store.data_ptr(), tuple(self._store.shape), self._store.stride(0), self._id_base, self._id_stride)
+        if key != self._bound_key:
+            self._engine.bind(self._store, self._id_base, self._id_stride)
+            self._bound_key = key
+        return self._engine
+
+    def _local_search(self, allqueries: torch.Tensor, topk: int, normalize: bool = False
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Fused score + select over this rank's shard -> (fp32 scores [B,k], global ids [B,k])."""
+        n_local = 0 if self._store is None else int(self._store.shape[0])
+        if topk > n_local:
+            raise RuntimeError("selected index k out of range")  # torch.topk's message, src/index.py:119
+        return self._get_engine().search(allqueries, topk, normalize=normalize)
+
+    def _merge_lists(self, scores: torch.Tensor, ids: torch.Tensor, topk: int):
+        from .engine import merge_topk
+        return merge_topk(scores, ids, topk)
+
+    @torch.no_grad()
+    def search(self, queries: torch.Tensor, topk: int, normalize: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Tensor-native distributed search: this rank's queries -> (scores fp32 [b,k], global ids [b,k]).
+
+        All ranks must call it together (like the reference's search_knn).  Steps: all-gather
+        queries -> local fused search -> one all-gather of candidates -> device merge -> own rows.
+        """
+        w, r = dist_utils.get_world_size(), dist_utils.get_rank()
+        if w == 1:
+            if queries.shape[0] == 0:
+                dev = queries.device
+                return torch.empty(0, topk, device=dev), torch.empty(0, topk, dtype=torch.int64, device=dev)
+            return self._local_search(queries, topk, normalize)
+        sizes = dist_utils.get_varsize(queries)                                    # src/index.py:129
+        allqueries = dist_utils.varsize_all_gather(queries, sizes)                 # src/index.py:128
+        offs = np.cumsum([0] + sizes)
+        if allqueries.shape[0] == 0:
+            return (torch.empty(0, topk, device=queries.device),
+                    torch.empty(0, topk, dtype=torch.int64, device=queries.device))
+        ls, li = self._local_search(allqueries, topk, normalize)                   # src/index.py:132
+        gs, gi = dist_utils.all_gather_candidates(ls, li)                          # replaces :139-142
+        ms, mi = self._merge_lists(gs, gi, topk)                                   # replaces :143-157
+        sl = slice(int(offs[r]), int(offs[r + 1]))
+        self._last_all = (mi, offs)
+        return ms[sl], mi[sl]
+
+    # ------------------------------------------------------------------ passage resolution
+    def _owner_and_local(self, gids: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        w = dist_utils.get_world_size()
+        if self._sharding == "round_robin":
+            return gids % w, gids // w
+        starts = np.cumsum([0] + list(self._all_counts))
+        owner = np.searchsorted(starts, gids, side="right") - 1
+        return owner, gids - starts[owner]
+
+    def _resolve_docs(self, my_ids: torch.Tensor) -> List[List[dict]]:
+        """global ids [b,k] -> passage dicts.  Single rank: local lookup.  Multi rank: every rank knows
+        the merged winners of *all* queries (the merge is replicated), so each owner publishes the
+        dicts it owns and one object all-gather delivers them (k winners, not W*k candidates)."""
+        w, r = dist_utils.get_world_size(), dist_utils.get_rank()
+        ids_np = my_ids.cpu().numpy()
+        if w == 1:
+            loc = (ids_np - self._id_base) // self._id_stride
+            return [[self.doc_map[int(x)] for x in row] for row in loc]
+        all_ids, _ = self._last_all
+        all_np = all_ids.cpu().numpy().reshape(-1)
+        owner, local = self._owner_and_local(all_np)
+        mine = {}
+        for g, l in zip(all_np[owner == r].tolist(), local[owner == r].tolist()):
+            mine[g] = self.doc_map[l]
+        merged = {}
+        for part in dist_utils.all_gather_object(mine):
+            merged.update(part)
+        return [[merged[int(g)] for g in row] for row in ids_np]
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def search_knn(self, queries, topk, return_embeddings: bool = False):
+        """Exhaustive inner-product k-NN (src/index.py:123-158).  Returns ``(docs, scores)`` — docs
+        first — as nested Python lists, rows sorted by descending score; with
+        ``return_embeddings=True`` also the passage embeddings ``[b, k, dim]`` like the
+        build_server twin (build_server/index.py:217-261)."""
+        scores, ids = self.search(queries, topk)
+        if scores.shape[0] == 0:
+            out = ([], [])
+            return out + (torch.empty(0, topk, self._store.shape[1], dtype=self.dtype),) if return_embeddings else out
+        docs = self._resolve_docs(ids)
+        if self.round_scores_to_index_dtype:
+            scores = scores.to(self.dtype)
+        scores_list = scores.float().tolist()
+        if return_embeddings:
+            return docs, scores_list, self._gather_embeddings(ids)
+        return docs, scores_list
+
+    def _gather_embeddings(self, ids: torch.Tensor) -> torch.Tensor:
+        """[b,k] global ids -> [b,k,dim] passage embeddings (build_server/index.py:228-229,254-255).
+        Multi rank: every owner fills the slots it owns, one all-reduce(sum) completes the tensor."""
+        w, r = dist_utils.get_world_size(), dist_utils.get_rank()
+        b, k = ids.shape
+        eng = self._get_engine()
+        if w == 1:
+            loc = (ids - self._id_base) // self._id_stride
+            return eng.gather_rows(loc).view(b, k, -1)
+        all_ids, offs = self._last_all
+        flat = all_ids.reshape(-1)
+        owner_np, local_np = self._owner_and_local(flat.cpu().numpy())
+        local = torch.from_numpy(np.where(owner_np == r, local_np, -1)).to(ids.device)
+        emb = eng.gather_rows(local).view(all_ids.shape[0], k, -1)   # rows with -1 come back as zeros
+        torch.distributed.all_reduce(emb)
+        return emb[int(offs[r]):int(offs[r + 1])]
+
+
+class B200IndexWithEmbeddings(B200Index):
+    """Twin of build_server/index.py:135-264 — ``search_knn`` returns (docs, scores, embeddings)."""
+
+    @torch.no_grad()
+    def search_knn(self, queries, topk):
+        return super().search_knn(queries, topk, return_embeddings=True)

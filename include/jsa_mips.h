@@ -122,6 +122,17 @@ int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k
 /* Number of kernels the last mips_search_local / mips_search_host on this handle launched. */
 int mips_last_launch_count(const mips_handle* h);
 
+/*
+ * Diagnostics (not used on the product path).  flags: 1 = skip the select epilogue, 2 = skip the
+ * MMAs (pure TMA streaming); results are meaningless with either set.  stats_dev: device array of
+ * [mips_num_sms()][mips_debug_num_stats()] uint64 per-CTA cycle counters the scan kernel fills
+ * (caller zeroes it), or NULL.  Counter order: producer wait, MMA wait(full), MMA wait(TMEM),
+ * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles.
+ */
+int mips_debug_config(mips_handle* h, int flags, void* stats_dev);
+int mips_debug_num_stats(void);
+int mips_num_sms(const mips_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,8 @@ struct mips_handle {
   void* io = nullptr;  // device staging for mips_search_host: queries | scores | ids
   size_t io_bytes = 0;
   int last_launches = 0;
+  int dbg_flags = 0;
+  unsigned long long* dbg_stats = nullptr;
   std::string err;
 };
 
@@ -107,7 +109,7 @@ int encode_rows_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t r
 }
 
 struct WsLayout {
-  size_t q_off, cand_off, ps_off, pi_off, total;
+  size_t q_off, cand_off, pk_off, seed_s_off, seed_i_off, total;
 };
 
 WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
@@ -117,8 +119,9 @@ WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
   size_t off = 0;
   w.q_off = off;    off += align_up(bpad * h->dim * 2, 1024);
   w.cand_off = off; off += align_up(grid * kNQ * kCap * sizeof(uint64_t), 1024);
-  w.ps_off = off;   off += align_up(grid * kNQ * static_cast<size_t>(max_k) * sizeof(float), 1024);
-  w.pi_off = off;   off += align_up(grid * kNQ * static_cast<size_t>(max_k) * sizeof(int64_t), 1024);
+  w.pk_off = off;   off += align_up(grid * kNQ * sizeof(int), 1024);
+  w.seed_s_off = off; off += align_up(static_cast<size_t>(kNQ) * max_k * sizeof(float), 1024);
+  w.seed_i_off = off; off += align_up(static_cast<size_t>(kNQ) * max_k * sizeof(int64_t), 1024);
   w.total = off;
   return w;
 }
@@ -261,17 +264,50 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   p.k = k;
   p.idesc = ptx::make_idesc_f16(kTileM, kNQ, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
   p.cand = reinterpret_cast<uint64_t*>(ws + w.cand_off);
-  p.part_scores = reinterpret_cast<float*>(ws + w.ps_off);
-  p.part_ids = reinterpret_cast<int64_t*>(ws + w.pi_off);
+  p.part_cnt = reinterpret_cast<int*>(ws + w.pk_off);
   p.id_base = h->id_base;
   p.id_stride = h->id_stride;
+  p.flags = h->dbg_flags;
+  p.stats = h->dbg_stats;
+
+  // Sampled pre-passes.  The k-th best score of any sample of the shard is a valid lower bound of
+  // the final k-th score, so it can seed the thresholds of a larger pass, which then appends only
+  // ~k * tiles / (grid * sample_tiles) candidates per (CTA, query): few enough that no list is ever
+  // compacted in-stream and the select kernel takes the raw lists.  levels[] holds the tiles per CTA
+  // of each pre-pass (the first is unseeded and one tile deep, so its lists hold <= 128 entries).
+  const int tiles_per_cta = (num_tiles + grid - 1) / grid;
+  int levels[4];
+  int n_levels = 0;
+  if (tiles_per_cta >= 4 && !(h->dbg_flags & kDbgNoSeed)) {
+    int64_t need = tiles_per_cta;
+    int tmp[4];
+    int nt = 0;
+    while (need > 1 && nt < 4) {
+      need = (need * k + static_cast<int64_t>(grid) * 150 - 1) / (static_cast<int64_t>(grid) * 150);
+      if (need < 1) need = 1;
+      tmp[nt++] = static_cast<int>(need);
+    }
+    for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
+  }
+  float* seed_scores = reinterpret_cast<float*>(ws + w.seed_s_off);
+  int64_t* seed_ids = reinterpret_cast<int64_t*>(ws + w.seed_i_off);
 
   for (int q0 = 0; q0 < batch; q0 += kNQ) {
     p.batch = batch - q0 < kNQ ? batch - q0 : kNQ;
     p.q_row0 = q0;
+    p.seed = nullptr;
+    for (int lv = 0; lv < n_levels; ++lv) {
+      ScanParams pp = p;
+      pp.num_tiles = levels[lv] * grid < num_tiles ? levels[lv] * grid : num_tiles;
+      pp.stats = nullptr;
+      CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, pp, grid, h->smem_bytes, st));
+      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, kNQ, k, 0, 1, seed_scores, seed_ids, st));
+      h->last_launches += 2;
+      p.seed = seed_scores;
+    }
     CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, grid, h->smem_bytes, st));
-    CUDA_TRY(h, launch_merge(p.part_scores, p.part_ids, grid, static_cast<int64_t>(kNQ) * k, p.batch, k, k,
-                             out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
+    CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.batch, k, h->id_base, h->id_stride,
+                              out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
     h->last_launches += 2;
   }
   return MIPS_OK;
@@ -333,5 +369,14 @@ int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k
 }
 
 int mips_last_launch_count(const mips_handle* h) { return h ? h->last_launches : 0; }
+
+int mips_debug_config(mips_handle* h, int flags, void* stats_dev) {
+  if (!h) return MIPS_EINVAL;
+  h->dbg_flags = flags;
+  h->dbg_stats = static_cast<unsigned long long*>(stats_dev);
+  return MIPS_OK;
+}
+int mips_debug_num_stats(void) { return kNumStats; }
+int mips_num_sms(const mips_handle* h) { return h ? h->num_sms : 0; }
 
 }  // extern "C"

@@ -16,6 +16,7 @@ constexpr int kQChunkBytes = kNQ * kKChunk * 2;     // 8 KiB query chunk (reside
 constexpr int kMaxStages = 8;
 constexpr int kCap = 512;        // candidate slots per (CTA, query) in the L2-resident candidate lists
 constexpr int kSortE = kCap / 32;  // keys per lane in the warp bitonic sort
+constexpr int kEmit = 256;       // a CTA hands at most this many candidates per query to the select kernel
 constexpr int kMaxK = 128;       // largest fused top-k
 constexpr int kMaxDim = 1024;
 constexpr int kScanThreads = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue/select
@@ -33,10 +34,18 @@ struct ScanParams {
   int q_row0;            // first row of this pass in the prepared query buffer
   uint32_t idesc;        // tcgen05 instruction descriptor (dtype dependent)
   uint64_t* cand;        // [grid][kNQ][kCap] packed (orderable score << 32 | ~row) keys
-  float* part_scores;    // [grid][kNQ][k]  per-CTA sorted partial top-k
-  int64_t* part_ids;     // [grid][kNQ][k]  global ids
+  int* part_cnt;         // [grid][kNQ] number of candidates each CTA leaves at the head of its lists
   int64_t id_base, id_stride;
+  const float* seed;     // optional [kNQ][k] sorted scores of the sampled pre-pass (NULL = none)
+  int flags;             // diagnostics: kDbgNoSelect / kDbgNoMma (results are then meaningless)
+  unsigned long long* stats;  // optional [grid][kNumStats] per-CTA cycle counters (NULL = off)
 };
+
+constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
+constexpr int kDbgNoMma = 2;
+constexpr int kDbgNoSeed = 4;    // disable the sampled pre-pass (thresholds start at -inf)     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
+enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
+            kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };
 
 // launchers (defined in scan.cu / merge.cu); return cudaError_t of the launch
 cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int batch, int batch_pad, int dim,
@@ -46,6 +55,8 @@ cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, co
 cudaError_t configure_scan(size_t smem_bytes);
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
                          int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st);
+cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int batch, int k, int64_t id_base,
+                          int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st);
 cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, const int64_t* rows, int64_t n,
                                void* out, cudaStream_t st);
 

@@ -138,6 +138,223 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-shard select: exact top-k of the (unsorted) candidate lists the scan kernel leaves behind.
+//
+// One CTA of 1024 threads per query.  Every CTA of the scan contributes <= kEmit packed keys
+// (orderable score << 32 | ~row, unique).  The score words are held in registers (kSelKPT per
+// thread); the k-th largest is found exactly by MSB-first bisection with block-wide counts; if
+// several candidates tie on that boundary score a second bisection over their row words decides
+// (smaller row wins).  The k winners are sorted by one warp and written as (fp32 score, int64 id).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kSelListsPerWarp = 5;                  // 32 warps * 5 lists = 160 >= 148 CTAs
+constexpr int kSelChunks = kEmit / 32;               // 8 keys of one list per lane
+constexpr int kSelKPT = kSelListsPerWarp * kSelChunks;  // 40 score words per thread
+constexpr int kSelMaxLists = kSelWarps * kSelListsPerWarp;
+
+template <int E>
+__device__ __forceinline__ void warp_sort_desc_u64(uint64_t (&key)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j < E) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & j) == 0) {
+            const int i = lane * E + e;
+            const bool desc = (i & k) == 0;
+            const uint64_t a = key[e], b = key[e ^ j];
+            const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
+            key[e] = desc ? hi : lo;
+            key[e ^ j] = desc ? lo : hi;
+          }
+        }
+      } else {
+        const int lmask = j / E;
+        const bool lower = (lane & lmask) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int i = lane * E + e;
+          const bool desc = (i & k) == 0;
+          const uint64_t a = key[e];
+          const uint64_t b = __shfl_xor_sync(0xffffffffu, a, lmask);
+          const bool keep_max = (desc == lower);
+          key[e] = keep_max ? (a > b ? a : b) : (a > b ? b : a);
+        }
+      }
+    }
+  }
+}
+
+// Block-wide MSB-first bisection over the non-zero 32-bit values v[] (kSelKPT per thread).
+// Invariant: at least kk values are >= prefix.  `prefix` enters with the bits common to every
+// candidate, `top_bit` is the first undecided bit, `n_ge` the number of values >= prefix.  Stops
+// as soon as no more than `stop_at` values remain >= prefix (they then fit the final sort), or
+// when all bits are decided (prefix is then exactly the kk-th largest value).
+__device__ __forceinline__ uint32_t block_bisect(const uint32_t (&v)[kSelKPT], int kk, uint32_t prefix, int top_bit,
+                                                 int& n_ge, int stop_at, int* s_cnt /*[32]*/) {
+  if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int b = top_bit; b >= 0 && n_ge > stop_at; --b) {
+    const uint32_t cand = prefix | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kSelKPT; ++j) c += v[j] >= cand ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt[b], c);
+    __syncthreads();
+    const int tot = s_cnt[b];
+    if (tot >= kk) { prefix = cand; n_ge = tot; }
+  }
+  __syncthreads();
+  return prefix;
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int k,
+                   int64_t id_base, int64_t id_stride, float* __restrict__ out_scores,
+                   int64_t* __restrict__ out_ids) {
+  __shared__ int s_cnt[32];
+  __shared__ int s_misc[4];       // [0] #greater, [1] #tied, [2] winner slots, [3] total candidates
+  __shared__ uint32_t s_bits[2];  // AND / OR of all candidate score words
+  __shared__ uint64_t s_win[kMaxK];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x < kMaxK) s_win[threadIdx.x] = 0;
+  if (threadIdx.x < 4) s_misc[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_bits[0] = 0xFFFFFFFFu; s_bits[1] = 0u; }
+  __syncthreads();
+
+  // warp w owns lists w, w+32, ...; lane owns positions lane, lane+32, ... of each (coalesced)
+  const uint64_t* lptr[kSelListsPerWarp];
+  uint32_t v[kSelKPT];
+  uint32_t and_v = 0xFFFFFFFFu, or_v = 0u;
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < kSelListsPerWarp; ++i) {
+    const int l = warp + i * kSelWarps;
+    int c = l < num_lists ? part_cnt[l * kNQ + q] : 0;
+    c = c > kEmit ? kEmit : c;
+    lptr[i] = cand + (static_cast<size_t>(l < num_lists ? l : 0) * kNQ + q) * kCap;
+#pragma unroll
+    for (int ch = 0; ch < kSelChunks; ++ch) {
+      const int pos = lane + 32 * ch;
+      uint32_t hi = 0u;
+      if (pos < c) {
+        hi = static_cast<uint32_t>(lptr[i][pos] >> 32);
+        and_v &= hi;
+        or_v |= hi;
+        ++mine;
+      }
+      v[i * kSelChunks + ch] = hi;
+    }
+  }
+  and_v = __reduce_and_sync(0xffffffffu, and_v);
+  or_v = __reduce_or_sync(0xffffffffu, or_v);
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) {
+    atomicAnd(&s_bits[0], and_v);
+    atomicOr(&s_bits[1], or_v);
+    if (mine) atomicAdd(&s_misc[3], mine);
+  }
+  __syncthreads();
+  const int total = s_misc[3];
+  // 1) raise a score-word threshold t_hi until at most kMaxK candidates are >= t_hi (or until it
+  //    is the exact k-th largest score word when many candidates tie)
+  uint32_t t_hi = 0;
+  int n_ge = total;
+  if (total > kMaxK) {  // block-uniform (k <= kMaxK <= total)
+    const uint32_t diff = s_bits[0] ^ s_bits[1];
+    if (diff == 0u) {
+      t_hi = s_bits[1];  // every candidate has the same score
+    } else {
+      const int top_bit = 31 - __clz(diff);
+      const uint32_t common = top_bit == 31 ? 0u : (s_bits[1] & ~((2u << top_bit) - 1u));
+      t_hi = block_bisect(v, k, common, top_bit, n_ge, kMaxK, s_cnt);
+    }
+  }
+  if (n_ge <= kMaxK) {
+    // 2a) common case: the <= kMaxK survivors go to the final sort, which orders full 64-bit keys
+    //     (score, then row) and therefore also resolves ties exactly
+#pragma unroll
+    for (int i = 0; i < kSelListsPerWarp; ++i) {
+#pragma unroll
+      for (int ch = 0; ch < kSelChunks; ++ch) {
+        const uint32_t hv = v[i * kSelChunks + ch];
+        if (hv != 0u && hv >= t_hi) {
+          const int slot = atomicAdd(&s_misc[2], 1);
+          if (slot < kMaxK) s_win[slot] = lptr[i][lane + 32 * ch];
+        }
+      }
+    }
+  } else {
+    // 2b) more than kMaxK candidates share the boundary score word t_hi (exact k-th largest):
+    //     everything above it wins, and a second bisection over the row words of the tied
+    //     candidates keeps the `need` smallest rows
+    int gt = 0;
+#pragma unroll
+    for (int j = 0; j < kSelKPT; ++j) gt += v[j] > t_hi ? 1 : 0;
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    if (lane == 0 && gt) atomicAdd(&s_misc[0], gt);
+#pragma unroll
+    for (int i = 0; i < kSelListsPerWarp; ++i) {
+#pragma unroll
+      for (int ch = 0; ch < kSelChunks; ++ch) {
+        const int j = i * kSelChunks + ch;
+        if (v[j] > t_hi) {
+          const int slot = atomicAdd(&s_misc[2], 1);
+          if (slot < kMaxK) s_win[slot] = lptr[i][lane + 32 * ch];
+        }
+        const bool tie = v[j] == t_hi && v[j] != 0u;
+        v[j] = tie ? static_cast<uint32_t>(lptr[i][lane + 32 * ch]) : 0u;
+      }
+    }
+    __syncthreads();
+    const int need = k - s_misc[0];  // >= 1
+    int n_tie = n_ge - s_misc[0];
+    const uint32_t t_lo = block_bisect(v, need, 0u, 31, n_tie, 0, s_cnt);  // exact need-th largest row word
+#pragma unroll
+    for (int j = 0; j < kSelKPT; ++j) {
+      if (v[j] != 0u && v[j] >= t_lo) {
+        const int slot = atomicAdd(&s_misc[2], 1);
+        if (slot < kMaxK) s_win[slot] = (static_cast<uint64_t>(t_hi) << 32) | v[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  uint64_t w[kMaxK / 32];
+#pragma unroll
+  for (int e = 0; e < kMaxK / 32; ++e) w[e] = s_win[lane * (kMaxK / 32) + e];
+  warp_sort_desc_u64<kMaxK / 32>(w, lane);
+#pragma unroll
+  for (int e = 0; e < kMaxK / 32; ++e) {
+    const int pos = lane * (kMaxK / 32) + e;
+    if (pos < k) {
+      const bool ok = w[e] != 0;
+      const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(w[e]);
+      out_scores[static_cast<int64_t>(q) * k + pos] = ok ? ord_to_f32(static_cast<uint32_t>(w[e] >> 32)) : -INFINITY;
+      out_ids[static_cast<int64_t>(q) * k + pos] = ok ? id_base + static_cast<int64_t>(r) * id_stride : -1;
+    }
+  }
+}
+
+cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int batch, int k, int64_t id_base,
+                          int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  if (batch == 0) return cudaSuccess;
+  if (num_lists > kSelMaxLists) return cudaErrorInvalidValue;
+  select_topk_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, k, id_base, id_stride, out_scores,
+                                                    out_ids);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
                          int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (batch == 0) return cudaSuccess;

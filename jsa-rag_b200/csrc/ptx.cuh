@@ -53,6 +53,44 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// bar.red.or: barrier among `nthreads` threads that also ORs a predicate across them
+__device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred pi, po;\n\t"
+      "setp.ne.u32 pi, %3, 0;\n\t"
+      "barrier.cta.red.or.pred po, %1, %2, pi;\n\t"
+      "selp.u32 %0, 1, 0, po;\n\t}"
+      : "=r"(out)
+      : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return out != 0;
+}
+// Predicated shared-memory atomic add (inline PTX so the compiler neither warp-aggregates nor
+// serialises it against its neighbours); returns the old value, 0 when not executed.
+__device__ __forceinline__ int atoms_add_pred(uint32_t addr, int val, bool pred) {
+  int old;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %3, 0;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+      : "=r"(old)
+      : "r"(addr), "r"(val), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return old;
+}
+// One lane of the (converged) warp is elected; returns true on that lane only.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
@@ -119,6 +157,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+// One fp32 column for the warp's 32 lanes; the column is a runtime value.
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
 
 // ------------------------------------------------------------------ UMMA descriptors

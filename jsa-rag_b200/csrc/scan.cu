@@ -24,85 +24,98 @@
 namespace mips {
 
 // ------------------------------------------------------------------------------------------------
-// Warp-wide bitonic sort, descending, of 32*E 64-bit keys; key i lives in lane i/E, slot i%E.
+// Warp-level exact selection over 32*E candidates held E per lane (no sorting).
 // ------------------------------------------------------------------------------------------------
+// k-th largest of the 32*E unsigned values v (0 = "not a candidate", never selected): MSB-first
+// bisection with one warp-wide population count per bit.  Requires >= kk non-zero values.
 template <int E>
-__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[E], int lane) {
-  constexpr int N = 32 * E;
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&v)[E], int kk) {
+  uint32_t prefix = 0;
+#pragma unroll 1
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t cand = prefix | (1u << b);
+    int c = 0;
 #pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j >= 1; j >>= 1) {
-      if (j < E) {  // partner in the same lane
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          if ((e & j) == 0) {
-            const int i = lane * E + e;
-            const bool desc = (i & k) == 0;
-            const uint64_t a = key[e], b = key[e ^ j];
-            const uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
-            key[e] = desc ? hi : lo;
-            key[e ^ j] = desc ? lo : hi;
-          }
-        }
-      } else {  // partner in lane ^ (j / E)
-        const int lmask = j / E;
-        const bool lower = (lane & lmask) == 0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int i = lane * E + e;
-          const bool desc = (i & k) == 0;
-          const uint64_t a = key[e];
-          const uint64_t b = __shfl_xor_sync(0xffffffffu, a, lmask);
-          const bool keep_max = (desc == lower);
-          key[e] = keep_max ? (a > b ? a : b) : (a > b ? b : a);
-        }
-      }
-    }
+    for (int e = 0; e < E; ++e) c += (v[e] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= kk) prefix = cand;
   }
+  return prefix;
 }
 
 __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
   return (static_cast<uint64_t>(f32_to_ord(score)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - row);
 }
 
-// Sort candidate list q (c valid entries) descending, keep the best `k` at its head, update the
-// query's threshold.  Returns the sorted keys in `key` (position i = lane*E + e).  Whole warp.
+// Keeps exactly the k best (largest-key) of the c > k candidates of one list, in place and
+// unsorted, and publishes the k-th best as the query's new threshold.  Keys are unique (they
+// embed the row), so "key >= k-th largest key" selects exactly k entries.  Whole warp.
 __device__ __forceinline__ void compact_list(uint64_t* __restrict__ list, int c, int k, int lane,
-                                             uint64_t (&key)[kSortE], uint64_t* thrkey_s, float* thr_s, int* cnt_s,
-                                             int q) {
+                                             uint64_t* thrkey_s, float* thr_s, int* cnt_s, int q) {
+  uint64_t key[kSortE];
+  uint32_t hi[kSortE];
   const ulonglong2* src = reinterpret_cast<const ulonglong2*>(list + lane * kSortE);
 #pragma unroll
   for (int e = 0; e < kSortE; e += 2) {
-    ulonglong2 v = src[e >> 1];
+    const ulonglong2 v = src[e >> 1];
     const int i = lane * kSortE + e;
     key[e] = (i < c) ? v.x : 0ull;
     key[e + 1] = (i + 1 < c) ? v.y : 0ull;
   }
-  warp_sort_desc<kSortE>(key, lane);
-  // write back the head (positions < kMaxK); only the first min(c, k) are meaningful afterwards
-  if (lane * kSortE < kMaxK) {
-    ulonglong2* dst = reinterpret_cast<ulonglong2*>(list + lane * kSortE);
 #pragma unroll
-    for (int e = 0; e < kSortE; e += 2) dst[e >> 1] = make_ulonglong2(key[e], key[e + 1]);
+  for (int e = 0; e < kSortE; ++e) hi[e] = static_cast<uint32_t>(key[e] >> 32);
+  // 1) k-th largest score image
+  const uint32_t t_hi = warp_kth_largest<kSortE>(hi, k);
+  // 2) among entries tied on the score, the (k - #greater)-th largest low word (= smallest rows)
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int e = 0; e < kSortE; ++e) {
+    gt += hi[e] > t_hi ? 1 : 0;
+    eq += hi[e] == t_hi ? 1 : 0;
   }
-  if (c >= k) {
-    uint64_t kth = 0;
+  gt = __reduce_add_sync(0xffffffffu, gt);
+  eq = __reduce_add_sync(0xffffffffu, eq);
+  const int need = k - gt;  // 1 <= need <= eq
+  uint32_t t_lo;
+  if (need == eq) {  // common case: every tied entry is kept -> threshold is the smallest tied low word
+    uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
     for (int e = 0; e < kSortE; ++e)
-      if (e == ((k - 1) % kSortE)) kth = key[e];
-    kth = __shfl_sync(0xffffffffu, kth, (k - 1) / kSortE);
-    if (lane == 0) {
-      thrkey_s[q] = kth;
-      thr_s[q] = ord_to_f32(static_cast<uint32_t>(kth >> 32));
-      cnt_s[q] = k;
-    }
+      if (hi[e] == t_hi) m = min(m, static_cast<uint32_t>(key[e]));
+    t_lo = __reduce_min_sync(0xffffffffu, m);
+  } else {
+    uint32_t lo[kSortE];
+#pragma unroll
+    for (int e = 0; e < kSortE; ++e) lo[e] = hi[e] == t_hi ? static_cast<uint32_t>(key[e]) : 0u;
+    t_lo = warp_kth_largest<kSortE>(lo, need);
+  }
+  const uint64_t thrkey = (static_cast<uint64_t>(t_hi) << 32) | t_lo;
+  // 3) stream compaction of the keepers to the head of the list
+  int mine = 0;
+#pragma unroll
+  for (int e = 0; e < kSortE; ++e) mine += key[e] >= thrkey ? 1 : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  int pos = incl - mine;
+#pragma unroll
+  for (int e = 0; e < kSortE; ++e)
+    if (key[e] >= thrkey) list[pos++] = key[e];
+  if (lane == 0) {
+    thrkey_s[q] = thrkey;
+    thr_s[q] = ord_to_f32(t_hi);
+    cnt_s[q] = k;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // The scan kernel
 // ------------------------------------------------------------------------------------------------
+#define SCORE(q) __uint_as_float((q) < 32 ? r0[(q)&31] : r1[(q)&31])
+
 __global__ void __launch_bounds__(kScanThreads, 1)
 mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_q,
                  const ScanParams p) {
@@ -149,8 +162,11 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kNQ) {
     const int q = threadIdx.x - 64;
     const bool live = q < p.batch;  // padded query columns never pass the filter
-    thr_s[q] = live ? -INFINITY : INFINITY;
-    thrkey_s[q] = live ? 0ull : ~0ull;
+    // initial threshold: the k-th best score of the sampled pre-pass when there is one (valid lower
+    // bound of the final k-th score), else -inf
+    const float seed = p.seed ? p.seed[static_cast<size_t>(q) * p.k + (p.k - 1)] : -INFINITY;
+    thr_s[q] = live ? seed : INFINITY;
+    thrkey_s[q] = live ? (static_cast<uint64_t>(f32_to_ord(seed)) << 32) : ~0ull;
     cnt_s[q] = 0;
   }
   if (warp == 1) {
@@ -164,148 +180,234 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
 
   const int first_tile = blockIdx.x;
   const int tile_step = gridDim.x;
+  // optional per-CTA cycle counters (diagnostics; zeroed by the host)
+  const bool want_stats = p.stats != nullptr;
+  unsigned long long* my_stats = want_stats ? p.stats + static_cast<size_t>(blockIdx.x) * kNumStats : nullptr;
+  const long long t_start = clock64();
+  long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, st_e = 0;
+  int st_m = 0, st_n = 0;
 
+  // Roles run warp-uniformly (all 32 lanes take the same path and wait on the same barriers);
+  // only the asynchronous issue instructions are predicated on one elected lane.  This keeps
+  // addresses and descriptors in uniform registers and the issue loops short.
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_qfull, nk * kQChunkBytes);
       for (int kc = 0; kc < nk; ++kc)
         ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, kc * kKChunk, p.q_row0, ptx::kEvictLast);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = first_tile; t < p.num_tiles; t += tile_step) {
-        for (int kc = 0; kc < nk; ++kc) {
-          ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = first_tile; t < p.num_tiles; t += tile_step) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const long long w0 = want_stats ? clock64() : 0;
+        ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        if (want_stats) st_a += clock64() - w0;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
           ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * kStageBytes, kc * kKChunk, t * kTileM,
                            ptx::kEvictFirst);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
+    if (want_stats && lane == 0) my_stats[kStProdWait] = st_a;
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      ptx::mbar_wait(bar_qfull, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = first_tile; t < p.num_tiles; t += tile_step, ++it) {
-        const int buf = it & 1;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+    ptx::mbar_wait(bar_qfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const bool no_mma = (p.flags & kDbgNoMma) != 0;
+    for (int t = first_tile; t < p.num_tiles; t += tile_step, ++it) {
+      const int buf = it & 1;
+      long long w0 = want_stats ? clock64() : 0;
+      ptx::mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+      if (want_stats) st_b += clock64() - w0;
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * kNQ;
+      for (int kc = 0; kc < nk; ++kc) {
+        w0 = want_stats ? clock64() : 0;
+        ptx::mbar_wait(bar_full + 8 * stage, phase);
+        if (want_stats) st_a += clock64() - w0;
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kNQ;
-        for (int kc = 0; kc < nk; ++kc) {
-          ptx::mbar_wait(bar_full + 8 * stage, phase);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = st_smem + stage * kStageBytes;
-          const uint32_t b_addr = q_smem + kc * kQChunkBytes;
+        if (ptx::elect_one()) {
+          if (no_mma) {
+            ptx::mbar_arrive(bar_empty + 8 * stage);
+            if (kc == nk - 1) ptx::mbar_arrive(bar_tfull + 8 * buf);
+          } else {
+            // K-major SWIZZLE_128B descriptors; advancing K by 16 elements = +32 bytes (= +2 in the
+            // 16-byte-granular start-address field) inside the 128-byte swizzle row
+            const uint64_t da = ptx::make_kmajor_sw128_desc(st_smem + stage * kStageBytes);
+            const uint64_t db = ptx::make_kmajor_sw128_desc(q_smem + kc * kQChunkBytes);
 #pragma unroll
-          for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4) {
-            // advancing K by 16 elements = 32 bytes inside the 128-byte swizzle row
-            const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + k4 * 32);
-            const uint64_t db = ptx::make_kmajor_sw128_desc(b_addr + k4 * 32);
-            ptx::umma_f16(d_tmem, da, db, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
+              ptx::umma_f16(d_tmem, da + 2 * k4, db + 2 * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+            ptx::umma_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs retire
+            if (kc == nk - 1) ptx::umma_commit(bar_tfull + 8 * buf);
           }
-          ptx::umma_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs retire
-          if (kc == nk - 1) ptx::umma_commit(bar_tfull + 8 * buf);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
+    if (want_stats && lane == 0) { my_stats[kStMmaWaitFull] = st_a; my_stats[kStMmaWaitTmem] = st_b; }
   } else {
     // =========================== epilogue / select ===========================
     const int ew = warp - 2;        // 0..3: which 16 queries this warp compacts
     const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint64_t* my_cand = p.cand + static_cast<size_t>(blockIdx.x) * kNQ * kCap;
-    uint64_t key[kSortE];
+    const bool no_select = (p.flags & kDbgNoSelect) != 0;
+    const uint32_t cnt_addr = ptx::smem_u32(cnt_s);
 
     int it = 0;
     for (int t = first_tile; t < p.num_tiles; t += tile_step, ++it) {
       const int buf = it & 1;
+      long long w0 = want_stats ? clock64() : 0;
       ptx::mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      if (want_stats) { const long long w1 = clock64(); st_a += w1 - w0; w0 = w1; }
       ptx::tc_fence_after();
       uint32_t r0[32], r1[32];
       ptx::tmem_ld_32x32b_x32(t_lane + buf * kNQ, r0);
       ptx::tmem_ld_32x32b_x32(t_lane + buf * kNQ + 32, r1);
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);  // accumulators are in registers now
+      if (want_stats) { const long long w1 = clock64(); st_d += w1 - w0; w0 = w1; }
+      if (no_select) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+        continue;
+      }
 
       const int64_t row = static_cast<int64_t>(t) * kTileM + quarter * 32 + lane;
       const bool valid = row < p.n_local;
+      const uint32_t row32 = static_cast<uint32_t>(row);
+      bool need_compact = false;
 
-      // fast filter: does any of my 64 scores reach its query's threshold?
-      bool any = false;
+      // ---- select ----
+      // A (static, ~2 instructions per score): per-thread bitmask of the queries whose running
+      //   threshold this passage reaches, OR-reduced over the warp into the set of non-empty queries.
+      // B (dynamic, compact code, 4 queries per round): the score column of each non-empty query is
+      //   re-read from TMEM (tcgen05.ld x1 takes a runtime column, registers cannot be indexed
+      //   dynamically), the exact 64-bit key test decides score ties by row, lanes 0..3 reserve
+      //   slots with ONE shared-memory atomic instruction, and the survivors are stored.
+      // Keeping B out of the unrolled code keeps the per-tile loop inside the instruction cache.
       const float4* thr4 = reinterpret_cast<const float4*>(thr_s);
+      const uint32_t lt_mask = (1u << lane) - 1u;
+      uint32_t pm0 = 0, pm1 = 0;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float4 th = thr4[g];
-        any |= __uint_as_float(r0[4 * g + 0]) >= th.x;
-        any |= __uint_as_float(r0[4 * g + 1]) >= th.y;
-        any |= __uint_as_float(r0[4 * g + 2]) >= th.z;
-        any |= __uint_as_float(r0[4 * g + 3]) >= th.w;
+        if (__uint_as_float(r0[4 * g + 0]) >= th.x) pm0 |= 1u << (4 * g + 0);
+        if (__uint_as_float(r0[4 * g + 1]) >= th.y) pm0 |= 1u << (4 * g + 1);
+        if (__uint_as_float(r0[4 * g + 2]) >= th.z) pm0 |= 1u << (4 * g + 2);
+        if (__uint_as_float(r0[4 * g + 3]) >= th.w) pm0 |= 1u << (4 * g + 3);
       }
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float4 th = thr4[8 + g];
-        any |= __uint_as_float(r1[4 * g + 0]) >= th.x;
-        any |= __uint_as_float(r1[4 * g + 1]) >= th.y;
-        any |= __uint_as_float(r1[4 * g + 2]) >= th.z;
-        any |= __uint_as_float(r1[4 * g + 3]) >= th.w;
+        if (__uint_as_float(r1[4 * g + 0]) >= th.x) pm1 |= 1u << (4 * g + 0);
+        if (__uint_as_float(r1[4 * g + 1]) >= th.y) pm1 |= 1u << (4 * g + 1);
+        if (__uint_as_float(r1[4 * g + 2]) >= th.z) pm1 |= 1u << (4 * g + 2);
+        if (__uint_as_float(r1[4 * g + 3]) >= th.w) pm1 |= 1u << (4 * g + 3);
       }
-      if (any && valid) {
-        const uint32_t row32 = static_cast<uint32_t>(row);
+      if (!valid) pm0 = pm1 = 0u;
+      uint32_t ne0 = __reduce_or_sync(0xffffffffu, pm0);
+      uint32_t ne1 = __reduce_or_sync(0xffffffffu, pm1);
+#pragma unroll 1
+      while ((ne0 | ne1) != 0u) {  // warp-uniform
+        int qs[4];
 #pragma unroll
-        for (int q = 0; q < kNQ; ++q) {
-          const float s = __uint_as_float(q < 32 ? r0[q & 31] : r1[q & 31]);
-          if (s >= thr_s[q]) {
-            const uint64_t kk = make_key(s, row32);
-            if (kk > thrkey_s[q]) {  // exact (score desc, row asc) order against the current k-th best
-              const int pos = atomicAdd(&cnt_s[q], 1);
-              my_cand[q * kCap + pos] = kk;
-            }
+        for (int u = 0; u < 4; ++u) {
+          if (ne0 != 0u) { qs[u] = __ffs(ne0) - 1; ne0 &= ne0 - 1u; }
+          else if (ne1 != 0u) { qs[u] = 32 + __ffs(ne1) - 1; ne1 &= ne1 - 1u; }
+          else qs[u] = -1;
+        }
+        uint32_t sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sv[u] = ptx::tmem_ld_32x32b_x1(t_lane + buf * kNQ + (qs[u] < 0 ? 0 : qs[u]));
+        ptx::tmem_ld_wait();
+        uint64_t kk[4];
+        uint32_t m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = qs[u] < 0 ? 0 : qs[u];
+          const uint32_t bits = q < 32 ? pm0 : pm1;
+          const bool mine = qs[u] >= 0 && ((bits >> (q & 31)) & 1u);
+          kk[u] = make_key(__uint_as_float(sv[u]), row32);
+          m[u] = __ballot_sync(0xffffffffu, mine && kk[u] > thrkey_s[q]);
+        }
+        const uint32_t mym = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : lane == 3 ? m[3] : 0u;
+        const int myq = lane == 0 ? qs[0] : lane == 1 ? qs[1] : lane == 2 ? qs[2] : qs[3];
+        int old = 0;
+        if (mym != 0u) old = atomicAdd(&cnt_s[myq], __popc(mym));  // lanes 0..3, distinct addresses
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int basep = __shfl_sync(0xffffffffu, old, u);
+          if ((m[u] >> lane) & 1u) {
+            const int pos = basep + __popc(m[u] & lt_mask);
+            my_cand[qs[u] * kCap + pos] = kk[u];
+            need_compact |= pos >= kCap - kTileM;
+            ++st_n;
           }
         }
       }
-      // all appends of this tile are done -> lists that could overflow on the next tile are compacted
-      ptx::named_bar_sync(1, 128);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);  // TMEM buffer may be overwritten now
+      // all appends of this tile are done; lists that could overflow during the next tile are
+      // compacted (one barrier with an OR-reduction tells every warp whether any list needs it)
+      if (want_stats) { const long long w1 = clock64(); st_b += w1 - w0; w0 = w1; }
+      const bool do_compact = ptx::named_bar_red_or(1, 128, need_compact);
+      if (want_stats) { const long long w1 = clock64(); st_e += w1 - w0; w0 = w1; }
+      if (do_compact) {
+#pragma unroll 1
+        for (int i = 0; i < kNQ / 4; ++i) {
+          const int q = ew * (kNQ / 4) + i;
+          const int c = cnt_s[q];
+          if (c > kCap - kTileM) {
+            compact_list(my_cand + q * kCap, c, p.k, lane, thrkey_s, thr_s, cnt_s, q);
+            ++st_m;
+          }
+        }
+        ptx::named_bar_sync(1, 128);
+        if (want_stats) st_c += clock64() - w0;
+      }
+    }
+
+    // ---------------- final: publish this CTA's candidate counts ----------------
+    // The candidate lists stay where they are (L2-resident workspace); the select kernel reads
+    // them directly.  Only lists longer than kEmit are first cut down to their best k.
+    if (!no_select) {
 #pragma unroll 1
       for (int i = 0; i < kNQ / 4; ++i) {
         const int q = ew * (kNQ / 4) + i;
-        const int c = cnt_s[q];
-        if (c > kCap - kTileM) compact_list(my_cand + q * kCap, c, p.k, lane, key, thrkey_s, thr_s, cnt_s, q);
-      }
-      ptx::named_bar_sync(1, 128);
-    }
-
-    // ---------------- final: sorted per-CTA top-k for every query ----------------
-#pragma unroll 1
-    for (int i = 0; i < kNQ / 4; ++i) {
-      const int q = ew * (kNQ / 4) + i;
-      const int c = cnt_s[q];
-      compact_list(my_cand + q * kCap, c, p.k, lane, key, thrkey_s, thr_s, cnt_s, q);
-      const int nvalid = c < p.k ? c : p.k;
-      float* out_s = p.part_scores + (static_cast<size_t>(blockIdx.x) * kNQ + q) * p.k;
-      int64_t* out_i = p.part_ids + (static_cast<size_t>(blockIdx.x) * kNQ + q) * p.k;
-#pragma unroll
-      for (int e = 0; e < kSortE; ++e) {
-        const int pos = lane * kSortE + e;
-        if (pos < p.k) {
-          const bool ok = pos < nvalid;
-          const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(key[e]);
-          out_s[pos] = ok ? ord_to_f32(static_cast<uint32_t>(key[e] >> 32)) : -INFINITY;
-          out_i[pos] = ok ? p.id_base + static_cast<int64_t>(r) * p.id_stride : -1;
+        int c = cnt_s[q];
+        if (c > kEmit) {
+          compact_list(my_cand + q * kCap, c, p.k, lane, thrkey_s, thr_s, cnt_s, q);
+          c = p.k;
+          ++st_m;
         }
+        if (lane == 0) p.part_cnt[static_cast<size_t>(blockIdx.x) * kNQ + q] = c;
       }
     }
+    if (want_stats && lane == 0) {
+      atomicAdd(&my_stats[kStEpiWaitTmem], static_cast<unsigned long long>(st_a));
+      atomicAdd(&my_stats[kStEpiSelect], static_cast<unsigned long long>(st_b));
+      atomicAdd(&my_stats[kStEpiCompact], static_cast<unsigned long long>(st_c));
+      atomicAdd(&my_stats[kStNumCompact], static_cast<unsigned long long>(st_m));
+      atomicAdd(&my_stats[kStEpiLd], static_cast<unsigned long long>(st_d));
+      atomicAdd(&my_stats[kStEpiBar], static_cast<unsigned long long>(st_e));
+    }
+    if (want_stats) atomicAdd(&my_stats[kStNumAppend], static_cast<unsigned long long>(st_n));
   }
 
   // ---------------- teardown ----------------
+  if (want_stats && threadIdx.x == 0) my_stats[kStTotal] = clock64() - t_start;
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -313,6 +415,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+#undef SCORE
 
 cudaError_t configure_scan(size_t smem_bytes) {
   return cudaFuncSetAttribute(mips_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

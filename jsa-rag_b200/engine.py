@@ -109,6 +109,23 @@ class MipsEngine:
         N.check(rc, self._h, "mips_search_host")
         return scores, ids
 
+    # ------------------------------------------------------------------ diagnostics
+    STAT_NAMES = ["prod_wait", "mma_wait_full", "mma_wait_tmem", "epi_wait_tmem", "epi_select", "epi_compact",
+                  "n_compact", "n_append", "total_cycles", "epi_ld", "epi_bar"]
+
+    def debug_config(self, flags: int = 0, collect_stats: bool = False):
+        """flags: 1 = skip select, 2 = skip MMAs (results meaningless).  Returns the stats tensor
+        [num_sms, 9] (uint64 as int64) the next scan launches accumulate into, or None."""
+        stats = None
+        if collect_stats:
+            stats = torch.zeros((self._lib.mips_num_sms(self._h), self._lib.mips_debug_num_stats()), dtype=torch.int64,
+                                device=self.device)
+        self._dbg_stats = stats
+        N.check(self._lib.mips_debug_config(self._h, int(flags),
+                                            ctypes.c_void_p(stats.data_ptr()) if stats is not None else None),
+                self._h, "mips_debug_config")
+        return stats
+
     def last_launch_count(self) -> int:
         return int(self._lib.mips_last_launch_count(self._h))
 

@@ -47,6 +47,26 @@ for c in cases:
         print("FAILED case", c, flush=True)
         break
 
+# ties: all-zero index (init_embeddings state) -> rows 0..k-1 with score 0; duplicated rows -> smallest ids win
+try:
+    z = torch.zeros(5000, 768, dtype=torch.float16, device=dev)
+    m = eng.MipsEngine(768, torch.float16, dev); m.bind(z)
+    q = torch.randn(7, 768, device=dev)
+    s_, i_ = m.search(q, 20); torch.cuda.synchronize()
+    print("zero index ok:", bool((i_ == torch.arange(20, device=dev)).all()), bool((s_ == 0).all()), flush=True)
+    e, q = make(3000, 768, 9, 5)
+    e2 = e.repeat(40, 1)            # every row appears 40 times: ids r, r+3000, ...
+    m.bind(e2)
+    s_, i_ = m.search(q, 100); torch.cuda.synchronize()
+    ref = (q.half().float() @ e2.float().T)
+    order = torch.argsort(-ref.double() * 1e6 + torch.arange(e2.shape[0], device=dev).double() * 1e-9, dim=1)[:, :100]
+    rs = torch.gather(ref, 1, order)
+    exact_ok = bool((torch.gather(ref, 1, i_) - s_).abs().max() < 1e-5)
+    print("dup index: ids equal to (score desc, id asc) order:", bool((order == i_).all()), "scores ok", exact_ok, flush=True)
+    m.close()
+except Exception:
+    traceback.print_exc()
+
 # timing
 try:
     n = int(os.environ.get("DBG_N", 4_000_000))

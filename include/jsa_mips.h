@@ -124,12 +124,16 @@ int mips_last_launch_count(const mips_handle* h);
 
 /*
  * Diagnostics (not used on the product path).  flags: 1 = skip the select epilogue, 2 = skip the
- * MMAs (pure TMA streaming); results are meaningless with either set.  stats_dev: device array of
+ * MMAs (pure TMA streaming) — results are meaningless with either set; 4 = no sampled pre-pass;
+ * 8 = time the scan launches.  stats_dev: device array of
  * [mips_num_sms()][mips_debug_num_stats()] uint64 per-CTA cycle counters the scan kernel fills
  * (caller zeroes it), or NULL.  Counter order: producer wait, MMA wait(full), MMA wait(TMEM),
  * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles.
  */
 int mips_debug_config(mips_handle* h, int flags, void* stats_dev);
+/* With flag 8 set, every full-shard scan launch is bracketed by CUDA events on the caller's stream;
+ * this returns (and clears) the recorded launch durations in milliseconds (at most 256 kept). */
+int mips_scan_times_ms(mips_handle* h, float* out, int max_out, int* n_out);
 int mips_debug_num_stats(void);
 int mips_num_sms(const mips_handle* h);
 

@@ -35,6 +35,7 @@ SYMBOLS = {
     "mips_last_launch_count": (c_int, [c_void_p]),
     "mips_debug_config": (c_int, [c_void_p, c_int, c_void_p]),
     "mips_debug_num_stats": (c_int, []),
+    "mips_scan_times_ms": (c_int, [c_void_p, POINTER(c_float), c_int, POINTER(c_int)]),
     "mips_num_sms": (c_int, [c_void_p]),
 }
 

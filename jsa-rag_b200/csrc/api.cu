@@ -34,6 +34,11 @@ struct mips_handle {
   int last_launches = 0;
   int dbg_flags = 0;
   unsigned long long* dbg_stats = nullptr;
+  // optional CUDA-event timing of the dominant kernel (the full-shard scan), for roofline reporting
+  static constexpr int kMaxTimed = 256;
+  cudaEvent_t ev0[kMaxTimed], ev1[kMaxTimed];
+  int n_timed = 0;
+  bool timing_ready = false;
   std::string err;
 };
 
@@ -183,6 +188,8 @@ void mips_destroy(mips_handle* h) {
   DeviceGuard g(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->io) cudaFree(h->io);
+  if (h->timing_ready)
+    for (int i = 0; i < mips_handle::kMaxTimed; ++i) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
   delete h;
 }
 
@@ -305,7 +312,10 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       h->last_launches += 2;
       p.seed = seed_scores;
     }
+    const bool timed = (h->dbg_flags & kDbgTimeScan) && h->timing_ready && h->n_timed < mips_handle::kMaxTimed;
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev0[h->n_timed], st));
     CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, grid, h->smem_bytes, st));
+    if (timed) { CUDA_TRY(h, cudaEventRecord(h->ev1[h->n_timed], st)); h->n_timed++; }
     CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.batch, k, h->id_base, h->id_stride,
                               out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
     h->last_launches += 2;
@@ -374,6 +384,28 @@ int mips_debug_config(mips_handle* h, int flags, void* stats_dev) {
   if (!h) return MIPS_EINVAL;
   h->dbg_flags = flags;
   h->dbg_stats = static_cast<unsigned long long*>(stats_dev);
+  h->n_timed = 0;
+  if ((flags & kDbgTimeScan) && !h->timing_ready) {
+    DeviceGuard g(h->device);
+    for (int i = 0; i < mips_handle::kMaxTimed; ++i) {
+      CUDA_TRY(h, cudaEventCreate(&h->ev0[i]));
+      CUDA_TRY(h, cudaEventCreate(&h->ev1[i]));
+    }
+    h->timing_ready = true;
+  }
+  return MIPS_OK;
+}
+
+int mips_scan_times_ms(mips_handle* h, float* out, int max_out, int* n_out) {
+  if (!h || !out || !n_out) return MIPS_EINVAL;
+  DeviceGuard g(h->device);
+  int n = h->n_timed < max_out ? h->n_timed : max_out;
+  for (int i = 0; i < n; ++i) {
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1[i]));
+    CUDA_TRY(h, cudaEventElapsedTime(&out[i], h->ev0[i], h->ev1[i]));
+  }
+  *n_out = n;
+  h->n_timed = 0;
   return MIPS_OK;
 }
 int mips_debug_num_stats(void) { return kNumStats; }

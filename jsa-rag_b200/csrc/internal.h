@@ -43,7 +43,8 @@ struct ScanParams {
 
 constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
 constexpr int kDbgNoMma = 2;
-constexpr int kDbgNoSeed = 4;    // disable the sampled pre-pass (thresholds start at -inf)     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
+constexpr int kDbgNoSeed = 4;
+constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)    // disable the sampled pre-pass (thresholds start at -inf)     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };
 

@@ -126,6 +126,13 @@ class MipsEngine:
                 self._h, "mips_debug_config")
         return stats
 
+    def scan_times_ms(self):
+        """Durations (ms) of the full-shard scan launches recorded since the last call (needs flag 8)."""
+        buf = (ctypes.c_float * 256)()
+        n = ctypes.c_int(0)
+        N.check(self._lib.mips_scan_times_ms(self._h, buf, 256, ctypes.byref(n)), self._h, "mips_scan_times_ms")
+        return [float(buf[i]) for i in range(n.value)]
+
     def last_launch_count(self) -> int:
         return int(self._lib.mips_last_launch_count(self._h))
 

@@ -38,6 +38,8 @@ class B200Index(object):
         self._device = device
         self._engine = None
         self._bound_key = None
+        self._any_rank_has_queries = False
+        self._last_all = None
         # global id of local row r = id_base + r * id_stride  (see _set_sharding)
         self._id_base, self._id_stride = 0, 1
         self._sharding = "round_robin"
@@ -186,6 +188,7 @@ class B200Index(object):
         queries -> local fused search -> one all-gather of candidates -> device merge -> own rows.
         """
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
+        self._any_rank_has_queries = False
         if w == 1:
             if queries.shape[0] == 0:
                 dev = queries.device
@@ -197,6 +200,7 @@ class B200Index(object):
         if allqueries.shape[0] == 0:
             return (torch.empty(0, topk, device=queries.device),
                     torch.empty(0, topk, dtype=torch.int64, device=queries.device))
+        self._any_rank_has_queries = True
         ls, li = self._local_search(allqueries, topk, normalize)                   # src/index.py:132
         gs, gi = dist_utils.all_gather_candidates(ls, li)                          # replaces :139-142
         ms, mi = self._merge_lists(gs, gi, topk)                                   # replaces :143-157
@@ -241,10 +245,13 @@ class B200Index(object):
         ``return_embeddings=True`` also the passage embeddings ``[b, k, dim]`` like the
         build_server twin (build_server/index.py:217-261)."""
         scores, ids = self.search(queries, topk)
+        # (every rank takes part in the passage exchange, also one whose own batch is empty)
+        docs = self._resolve_docs(ids) if (scores.shape[0] > 0 or self._any_rank_has_queries) else []
         if scores.shape[0] == 0:
-            out = ([], [])
-            return out + (torch.empty(0, topk, self._store.shape[1], dtype=self.dtype),) if return_embeddings else out
-        docs = self._resolve_docs(ids)
+            if return_embeddings:
+                emb = self._gather_embeddings(ids) if self._any_rank_has_queries else None
+                return [], [], (emb if emb is not None else torch.empty(0, topk, self._store.shape[1], dtype=self.dtype))
+            return [], []
         if self.round_scores_to_index_dtype:
             scores = scores.to(self.dtype)
         scores_list = scores.float().tolist()

@@ -1,0 +1,276 @@
+"""Parity of the sm_100a path (called through the C ABI) against the oracle and the golden vectors
+frozen from the unmodified reference.  Bar (BASELINE.json north_star): identical top-k passage-id
+sets except documented near-ties (score gap below 1e-3 relative), scores within 1e-3 relative —
+`oracle.flat_index_oracle.compare_topk` implements exactly that."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from oracle import flat_index_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3  # tolerance stated by north_star
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch.device("cuda:0")
+
+
+def _engine(eng, e, dtype=torch.float16, **kw):
+    m = eng.MipsEngine(e.shape[1], dtype, e.device)
+    m.bind(e, **kw)
+    return m
+
+
+def _synth(n, d, b, seed, dev, dtype=torch.float16):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    e = torch.empty(n, d, dtype=dtype, device=dev)
+    for s in range(0, n, 1 << 20):
+        c = torch.randn(min(1 << 20, n - s), d, generator=g, device=dev)
+        e[s:s + c.shape[0]] = torch.nn.functional.normalize(c, dim=1).to(dtype)
+    q = torch.nn.functional.normalize(torch.randn(b, d, generator=g, device=dev), dim=1)
+    return e, q
+
+
+def _torch_ref(e, q, k, dtype=torch.float16):
+    """fp32 scores of the stored operands on the same device + (score desc, id asc) order."""
+    s = q.to(dtype).float() @ e.float().T
+    order = torch.argsort(-s, dim=1, stable=True)[:, :k]
+    return torch.gather(s, 1, order), order
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_vectors_through_cabi(eng, dev, name):
+    g = load_golden(name)
+    k = int(g["k"])
+    e = torch.from_numpy(g["embeddings"]).to(dev)
+    m = _engine(eng, e)
+    s, i = m.search(torch.from_numpy(g["queries"]).to(dev), k)
+    exact = O.exact_scores(g["queries"], g["embeddings"])
+    rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), g["ids"], g["scores"].astype(np.float32), exact, rtol=RTOL)
+    assert rep["ok"], rep["errors"][:3]
+    # same through the HOST-buffer entry point of the C ABI
+    s2, i2 = m.search_host(torch.from_numpy(g["queries"]), k)
+    assert torch.equal(s2, s.cpu()) and torch.equal(i2, i.cpu())
+
+
+def test_drop_in_search_knn_matches_reference_outputs(eng, dev):
+    g = load_golden("flat_n1003_d768_b8_k20")
+    n = int(g["n"])
+    passages = [{"id": str(i), "title": f"t{i}", "text": f"passage {i}"} for i in range(n)]
+    idx = eng.B200Index()
+    idx.init_embeddings(passages, dim=768)
+    assert idx.embeddings.is_cuda and tuple(idx.embeddings.shape) == (768, n)
+    for a in range(0, n, 256):                                   # write site of src/rag.py:108-121
+        chunk = torch.from_numpy(g["embeddings"][a:a + 256]).to(dev)
+        idx.embeddings[:, a:a + chunk.shape[0]] = chunk.T
+    docs, scores = idx.search_knn(torch.from_numpy(g["queries"]).to(dev), 20)   # docs first (src/index.py:158)
+    assert len(docs) == 8 and len(docs[0]) == 20 and isinstance(docs[0][0], dict) and isinstance(scores[0][0], float)
+    ids = np.array([[int(d["id"]) for d in row] for row in docs])
+    exact = O.exact_scores(g["queries"], g["embeddings"])
+    rep = O.compare_topk(ids, np.array(scores), g["ids"], g["scores"].astype(np.float32), exact, rtol=RTOL)
+    assert rep["ok"], rep["errors"][:3]
+    # scores are returned fp16-rounded like the reference's: most are bit-identical to the golden ones
+    same = np.mean(np.sort(np.array(scores, dtype=np.float32), axis=1) == np.sort(g["scores"].astype(np.float32), axis=1))
+    assert same > 0.9
+    assert idx.search_knn(torch.empty(0, 768, device=dev), 20) == ([], [])          # empty batch
+    with pytest.raises(RuntimeError, match="selected index k out of range"):        # torch.topk's error
+        idx.search_knn(torch.from_numpy(g["queries"]).to(dev), n + 1)
+    d3, s3, emb = idx.search_knn(torch.from_numpy(g["queries"]).to(dev), 5, return_embeddings=True)
+    ids3 = torch.tensor([[int(d["id"]) for d in row] for row in d3])
+    assert tuple(emb.shape) == (8, 5, 768) and torch.equal(emb.cpu(), torch.from_numpy(g["embeddings"])[ids3])
+    tw = eng.B200IndexWithEmbeddings()
+    tw.init_embeddings(passages, dim=768)
+    tw.embeddings[:, :] = torch.from_numpy(g["embeddings"]).to(dev).T
+    assert len(tw.search_knn(torch.from_numpy(g["queries"]).to(dev), 5)) == 3       # build_server/index.py:261
+
+
+def test_save_load_roundtrip_on_device(eng, dev, tmp_path):
+    g = load_golden("flat_n300_d1024_b5_k10")
+    passages = [{"id": str(i)} for i in range(300)]
+    idx = eng.B200Index()
+    idx.init_embeddings(passages, dim=1024)
+    idx.embeddings[:, :] = torch.from_numpy(g["embeddings"]).to(dev).T
+    idx.save_index(str(tmp_path), 3)
+    idx2 = eng.B200Index()
+    idx2.load_index(str(tmp_path), 3)
+    d1, s1 = idx.search_knn(torch.from_numpy(g["queries"]).to(dev), 10)
+    d2, s2 = idx2.search_knn(torch.from_numpy(g["queries"]).to(dev), 10)
+    assert d1 == d2 and s1 == s2
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs, edge cases
+@pytest.mark.parametrize("n,d,b,k,dtype", [
+    (1, 768, 1, 1, torch.float16), (127, 768, 3, 127, torch.float16), (128, 768, 64, 128, torch.float16),
+    (129, 768, 65, 20, torch.float16), (5000, 1024, 7, 100, torch.float16), (30011, 768, 130, 10, torch.float16),
+    (60000, 768, 64, 100, torch.bfloat16), (148 * 128 * 5 + 77, 768, 33, 100, torch.float16),
+    (250000, 768, 64, 100, torch.float16), (20000, 64, 16, 50, torch.float16), (20000, 256, 5, 128, torch.bfloat16),
+])
+def test_matches_fp32_oracle_bitwise_ids(eng, dev, n, d, b, k, dtype):
+    """fp32-accumulated scores of identical stored operands: ids must agree with the (score desc,
+    id asc) order except where two fp32 scores differ by less than accumulation-order noise."""
+    e, q = _synth(n, d, b, 1000 + n % 97, dev, dtype)
+    m = _engine(eng, e, dtype)
+    s, i = m.search(q, k)
+    rs, ri = _torch_ref(e, q, k, dtype)
+    assert bool((s[:, 1:] <= s[:, :-1]).all()), "scores not sorted descending"
+    assert int(i.min()) >= 0 and int(i.max()) < n
+    got = torch.gather(q.to(dtype).float() @ e.float().T, 1, i)
+    assert float((s - got).abs().max()) <= 2e-6 * max(1.0, float(got.abs().max())) + 1e-6
+    exact = (q.to(dtype).double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]
+    assert rep["near_tie_diffs"] <= max(1, b * k // 200)
+
+
+def test_ties_are_broken_by_ascending_id(eng, dev):
+    z = torch.zeros(5000, 768, dtype=torch.float16, device=dev)          # init_embeddings() state: all scores 0
+    m = _engine(eng, z)
+    s, i = m.search(torch.randn(7, 768, device=dev), 20)
+    assert bool((s == 0).all()) and bool((i == torch.arange(20, device=dev)).all())
+    e, q = _synth(3000, 768, 9, 5, dev)
+    e2 = e.repeat(40, 1)                                                  # every row 40 times
+    m.bind(e2)
+    s, i = m.search(q, 100)
+    rs, ri = _torch_ref(e2, q, 100)
+    assert torch.equal(i, ri) and float((s - rs).abs().max()) < 1e-5
+
+
+def test_global_id_mapping_and_gather(eng, dev):
+    e, q = _synth(4096, 768, 4, 3, dev)
+    m = _engine(eng, e, id_base=3, id_stride=8)      # round-robin shard of rank 3 of 8 (src/index_io.py:41)
+    s, i = m.search(q, 10)
+    rs, ri = _torch_ref(e, q, 10)
+    assert torch.equal(i, ri * 8 + 3)
+    rows = m.gather_rows(ri)
+    assert torch.equal(rows.view(4, 10, 768), e[ri])
+    m.bind(e[:, :], id_base=1000, id_stride=1)       # contiguous shard starting at row 1000
+    assert torch.equal(m.search(q, 10)[1], ri + 1000)
+
+
+def test_query_dtypes_and_normalisation(eng, dev):
+    """allqueries.half() (src/index.py:118) for fp32 / bf16 / fp16 queries; normalize=True is
+    faiss.normalize_L2 on the queries only (build_server/server_start.py:142)."""
+    e, q = _synth(20000, 768, 12, 11, dev)
+    m = _engine(eng, e)
+    s32, i32 = m.search(q, 30)
+    s16, i16 = m.search(q.half(), 30)
+    assert torch.equal(i32, i16) and torch.equal(s32, s16)
+    sb, ib = m.search(q.bfloat16(), 30)
+    rs, ri = _torch_ref(e, q.bfloat16().float(), 30)
+    assert float((sb - rs).abs().max()) < 1e-5
+    scaled = q * torch.linspace(0.1, 30, 12, device=dev)[:, None]
+    sn, inn = m.search(scaled, 30, normalize=True)
+    d, i = O.server_search(scaled.cpu().numpy(), e.cpu().numpy(), 30)
+    exact = O.exact_scores(O.normalize_l2(scaled.cpu().numpy()), e.cpu().numpy(), q_dtype=None)
+    rep = O.compare_topk(inn.cpu().numpy(), sn.cpu().numpy(), i, d, exact, rtol=RTOL)
+    assert rep["ok"], rep["errors"][:3]
+    # non-contiguous (row-strided) queries
+    wide = torch.zeros(12, 1024, device=dev)
+    wide[:, :768] = q
+    s_str, i_str = m.search(wide[:, :768], 30)
+    assert torch.equal(i_str, i32)
+
+
+def test_error_codes_and_limits(eng, dev):
+    e, q = _synth(500, 768, 2, 1, dev)
+    m = _engine(eng, e)
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        m.search(q, 501)
+    with pytest.raises(ValueError):
+        m.search(q, eng._native.load().mips_max_k() + 1)
+    with pytest.raises(ValueError):
+        m.search(q[:, :100], 5)
+    with pytest.raises(ValueError):
+        m.bind(e.float())
+    s, i = m.search(q[:0], 5)
+    assert tuple(s.shape) == (0, 5)
+    fresh = eng.MipsEngine(768, torch.float16, dev)
+    with pytest.raises(RuntimeError, match="mips_bind_index"):
+        fresh.search(q, 5)
+    assert m.last_launch_count() == 0 and m.search(q, 5) and m.last_launch_count() >= 3
+
+
+def test_merge_kernel_matches_reference_merge(eng, dev):
+    """mips_merge_topk == concat per-rank blocks in rank order + torch.topk (src/index.py:143-157),
+    with (score desc, id asc) tie order."""
+    torch.manual_seed(0)
+    for L, b, k_in, k_out in [(8, 64, 100, 100), (2, 5, 20, 20), (4, 3, 128, 50), (1, 9, 10, 10), (16, 2, 7, 7)]:
+        s = torch.sort(torch.randn(L, b, k_in, device=dev), dim=2, descending=True).values
+        s[0, :, : min(3, k_in)] = s[L - 1, :, : min(3, k_in)]              # exact cross-list ties
+        s = torch.sort(s, dim=2, descending=True).values
+        ids = torch.stack([torch.randperm(100000, device=dev)[: b * k_in].view(b, k_in) + 100000 * l for l in range(L)])
+        ms, mi = eng.merge_topk(s, ids, k_out)
+        ref_s, ref_i = O.merge_rank_results(list(s.cpu()), list(ids.cpu()), k_out)
+        assert torch.equal(ms.cpu(), ref_s)
+        flat_s = s.permute(1, 0, 2).reshape(b, -1).cpu().double().numpy()
+        flat_i = ids.permute(1, 0, 2).reshape(b, -1).cpu().numpy()
+        want = np.stack([flat_i[r][np.lexsort((flat_i[r], -flat_s[r]))[:k_out]] for r in range(b)])
+        assert np.array_equal(mi.cpu().numpy(), want)
+    # padding entries (id < 0) are ignored
+    s = torch.tensor([[[3.0, 1.0, -float("inf")]], [[2.0, -float("inf"), -float("inf")]]], device=dev)
+    i = torch.tensor([[[5, 7, -1]], [[9, -1, -1]]], device=dev)
+    ms, mi = eng.merge_topk(s, i, 3)
+    assert mi.tolist() == [[5, 9, 7]] and ms.tolist() == [[3.0, 2.0, 1.0]]
+
+
+def test_emulated_shards_merge_to_the_global_answer(eng, dev):
+    """Row-sharding property (the 8-GPU layout on one device): merging the per-shard top-k of W
+    round-robin shards equals the top-k of the whole index, ids included."""
+    e, q = _synth(80000, 768, 64, 21, dev)
+    m = _engine(eng, e)
+    gs, gi = m.search(q, 100)
+    W = 8
+    parts = []
+    for r in range(W):
+        mr = _engine(eng, e[r::W].contiguous(), id_base=r, id_stride=W)
+        parts.append(mr.search(q, 100))
+    ms, mi = eng.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 100)
+    assert torch.equal(mi, gi) and torch.equal(ms, gs)
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def _properties(eng, dev, n, b, k, seed):
+    e, q = _synth(n, 768, b, seed, dev)
+    planted = torch.randint(0, n, (b,), device=dev, generator=torch.Generator(device=dev).manual_seed(seed + 1))
+    q = torch.nn.functional.normalize(e[planted].float() + 0.02 * q, dim=1)      # known nearest neighbours
+    m = _engine(eng, e)
+    s, i = m.search(q, k)
+    s2, i2 = m.search(q, k)
+    assert torch.equal(s, s2) and torch.equal(i, i2), "search is not deterministic / idempotent"
+    assert torch.equal(i[:, 0], planted), "planted nearest neighbour not ranked first"
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    assert all(len(set(r.tolist())) == k for r in i.cpu()), "duplicate ids"
+    # returned scores are the true inner products of the returned rows
+    got = torch.einsum("bd,bkd->bk", q.half().float(), e[i].float())
+    assert float((s - got).abs().max()) <= 2e-6 + 2e-6 * float(got.abs().max())
+    # no row of a random 2M-row sample beats the k-th returned score (completeness of the scan)
+    samp = torch.randint(0, n, (min(n, 2_000_000),), device=dev)
+    for a in range(0, samp.numel(), 1 << 19):
+        rows = samp[a:a + (1 << 19)]
+        sc = q.half().float() @ e[rows].float().T
+        better = sc > (s[:, -1:] * (1 + 1e-6) + 1e-7)
+        if better.any():
+            bq, bc = better.nonzero(as_tuple=True)
+            assert bool((i[bq] == rows[bc][:, None]).any(1).all()), "a better row is missing from the result"
+    return m, e, q
+
+
+def test_properties_at_shard_size(eng, dev):
+    _properties(eng, dev, 4_125_000, 64, 100, 7)          # one of 8 shards of the 33M index
+
+
+@pytest.mark.skipif(os.environ.get("JSA_SKIP_FULL_SIZE") == "1", reason="disabled by JSA_SKIP_FULL_SIZE")
+def test_properties_at_full_size(eng, dev):
+    """BASELINE configs[1]: 33M x 768 fp16 (50.7 GB), batch 64, top-100 on one B200."""
+    free, total = torch.cuda.mem_get_info()
+    if free < 70 * (1 << 30):
+        pytest.skip("not enough free device memory for the 33M x 768 index")
+    _properties(eng, dev, 33_000_000, 64, 100, 9)

@@ -1,0 +1,175 @@
+"""CPU-only tests of the host layer: C-ABI surface, storage / shard I/O compatible with the reference,
+loud failure without the CUDA device, and the world_size-2 plumbing over gloo."""
+import ctypes
+import importlib
+import json
+import os
+import pickle
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import ref_import
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_cabi_exports_every_declared_symbol(eng):
+    header = open(os.path.join(ROOT, "include", "jsa_mips.h")).read()
+    declared = set(re.findall(r"\b(mips_[a-z_0-9]+)\s*\(", header))
+    declared.discard("mips_handle")
+    assert {"mips_create", "mips_bind_index", "mips_search_local", "mips_merge_topk", "mips_gather_rows",
+            "mips_search_host", "mips_workspace_bytes", "mips_last_error", "mips_destroy"} <= declared
+    lib = ctypes.CDLL(eng._native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in jsa_mips.h but not exported"
+    assert set(eng._native.SYMBOLS) == declared, "ctypes table and header disagree"
+    n = eng._native.load()
+    assert n.mips_abi_version() == 1 and n.mips_max_k() >= 100 and n.mips_max_dim() >= 1024
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(eng):
+    n = eng._native.load()
+    h = ctypes.c_void_p()
+    rc = n.mips_create(ctypes.byref(h), 0, 768, 0)
+    assert rc == eng._native.MIPS_EUNSUPPORTED and "no CPU fallback" in eng._native.last_error(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        eng.MipsEngine(768)
+    idx = eng.B200Index()
+    idx.init_embeddings([{"id": str(i)} for i in range(10)], dim=768)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        idx.search_knn(torch.randn(2, 768), 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        eng.merge_topk(torch.zeros(2, 1, 4), torch.zeros(2, 1, 4, dtype=torch.int64), 4)
+
+
+def test_create_rejects_bad_arguments(eng):
+    n = eng._native.load()
+    h = ctypes.c_void_p()
+    assert n.mips_create(ctypes.byref(h), 0, 100, 0) == eng._native.MIPS_EINVAL   # dim not a multiple of 64
+    assert "multiple of 64" in eng._native.last_error(None)
+    assert n.mips_create(ctypes.byref(h), 0, 768, 7) == eng._native.MIPS_EINVAL   # unknown dtype
+    assert n.mips_create(None, 0, 768, 0) == eng._native.MIPS_EINVAL
+
+
+def test_storage_is_reference_shaped_view(eng):
+    idx = eng.B200Index(device="cpu")
+    assert idx.embeddings is None and idx.doc_map == {} and idx.is_index_trained()
+    passages = [{"id": str(i), "text": f"p{i}"} for i in range(37)]
+    idx.init_embeddings(passages, dim=768)
+    emb = idx.embeddings
+    assert tuple(emb.shape) == (768, 37) and emb.dtype == torch.float16 and float(emb.abs().sum()) == 0.0
+    x = torch.randn(10, 768)
+    idx.embeddings[:, 5:15] = x.T                 # src/rag.py:120
+    assert torch.equal(idx._store[5:15], x.half()) and torch.equal(idx.embeddings[:, 5:15], x.half().T)
+    assert idx._store.is_contiguous() and len(idx.doc_map) == 37 and idx.doc_map[3]["id"] == "3"
+    idx.embeddings = torch.randn(768, 12)         # attribute assignment like load_index in the reference
+    assert tuple(idx._store.shape) == (12, 768)
+
+
+def test_shard_files_match_reference_format(eng, tmp_path):
+    g = load_golden("flat_n1003_d768_b8_k20")
+    n = int(g["n"])
+    passages = [{"id": str(i), "title": f"t{i}", "text": f"passage {i}"} for i in range(n)]
+    idx = eng.B200Index(device="cpu")
+    idx.init_embeddings(passages, dim=768)
+    idx.embeddings[:, :] = torch.from_numpy(g["embeddings"]).T
+    idx.save_index(str(tmp_path), 4)
+    files = sorted(os.listdir(tmp_path))
+    assert files == [f"embeddings.{i}.pt" for i in range(4)] + [f"passages.{i}.pt" for i in range(4)]
+    at = 0
+    for i, width in enumerate([251, 251, 251, 250]):
+        t = torch.load(tmp_path / f"embeddings.{i}.pt")
+        assert tuple(t.shape) == (768, width) and t.dtype == torch.float16 and t.is_contiguous()
+        assert torch.equal(t, torch.from_numpy(g["embeddings"][at:at + width]).T)
+        with open(tmp_path / f"passages.{i}.pt", "rb") as f:
+            assert pickle.load(f) == passages[at:at + width]    # raw pickle, not torch.save (src/index.py:84-85)
+        at += width
+    idx2 = eng.B200Index(device="cpu")
+    idx2.load_index(str(tmp_path), 4)
+    assert torch.equal(idx2._store, idx._store) and idx2.doc_map == idx.doc_map and idx2._sharding == "contiguous"
+    # embeddings are always rewritten, passages only when missing / overwrite requested (src/index.py:82)
+    passages[0]["text"] = "changed"
+    idx.doc_map[0] = passages[0]
+    idx.save_index(str(tmp_path), 4)
+    with open(tmp_path / "passages.0.pt", "rb") as f:
+        assert pickle.load(f)[0]["text"] == "passage 0"
+    idx.save_index(str(tmp_path), 4, overwrite_saved_passages=True)
+    with open(tmp_path / "passages.0.pt", "rb") as f:
+        assert pickle.load(f)[0]["text"] == "changed"
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+def test_shard_files_interchange_with_live_reference(eng, tmp_path):
+    from oracle import make_golden
+    e16, q = make_golden.synth_inputs(203, 768, 2, seed=5)
+    _, _, ref_idx = make_golden.run_reference(e16, q, 5)
+    d_ref, d_ours = tmp_path / "ref", tmp_path / "ours"
+    d_ref.mkdir(), d_ours.mkdir()
+    ref_idx.save_index(str(d_ref), 2)                  # written by the unmodified reference
+    ours = eng.B200Index(device="cpu")
+    ours.load_index(str(d_ref), 2)
+    assert torch.equal(ours.embeddings, ref_idx.embeddings) and ours.doc_map == ref_idx.doc_map
+    ours.save_index(str(d_ours), 2)
+    for f in sorted(os.listdir(d_ref)):
+        if f.startswith("embeddings"):
+            assert torch.equal(torch.load(d_ref / f), torch.load(d_ours / f))
+            assert os.path.getsize(d_ref / f) == os.path.getsize(d_ours / f)
+        else:
+            assert open(d_ref / f, "rb").read() == open(d_ours / f, "rb").read()
+
+
+def test_load_passages_and_factory(eng, tmp_path):
+    p = tmp_path / "p.jsonl"
+    with open(p, "w") as f:
+        for i in range(7):
+            rec = {"id": str(i), "title": "T", "text": "x"}
+            if i % 2:
+                rec["section"] = "S"
+            f.write(json.dumps(rec) + "\n")
+    ps = eng.load_passages([str(p)])
+    assert len(ps) == 7 and ps[1]["title"] == "T: S" and ps[0]["title"] == "T"   # src/index_io.py:30-31
+    assert len(eng.load_passages([str(p)], maxload=3)) == 3
+
+    class Opt:
+        index_mode = "flat"; load_index_path = None; use_file_passages = False
+        passages = [str(p)]; max_passages = -1; retriever_model_path = "facebook/contriever"; save_index_n_shards = 1
+    index, passages = eng.load_or_initialize_index(Opt())
+    assert isinstance(index, eng.B200Index) and tuple(index.embeddings.shape) == (768, 7) and passages == ps
+    Opt.retriever_model_path = "BAAI/bge-large-en"
+    assert eng.load_or_initialize_index(Opt())[0].embeddings.shape[0] == 1024     # src/index_io.py:92
+    Opt.index_mode = "b200"
+    assert isinstance(eng.load_or_initialize_index(Opt())[0], eng.B200Index)
+    Opt.index_mode = "annoy"
+    with pytest.raises(ValueError, match="unsupported index mode"):
+        eng.load_or_initialize_index(Opt())
+    Opt.index_mode = "faiss"; Opt.faiss_index_type = "ivfpq"
+    with pytest.raises(ValueError):
+        eng.load_or_initialize_index(Opt())
+
+
+def test_candidate_packing_single_process(eng):
+    s = torch.randn(3, 5)
+    i = torch.randint(0, 1 << 40, (3, 5))
+    gs, gi = eng.dist_utils.all_gather_candidates(s, i)
+    assert torch.equal(gs[0], s) and torch.equal(gi[0], i)
+    assert eng.dist_utils.get_world_size() == 1 and eng.dist_utils.get_rank() == 0
+    assert torch.equal(eng.dist_utils.varsize_all_gather(s), s)
+
+
+@pytest.mark.parametrize("mode", ["round_robin", "contiguous"])
+def test_two_rank_search_over_gloo(mode, tmp_path):
+    import torch.multiprocessing as mp
+    import _dist_worker
+    mp.spawn(_dist_worker.worker, args=(2, _free_port(), str(tmp_path), mode), nprocs=2, join=True)

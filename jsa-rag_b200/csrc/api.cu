@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -24,7 +25,7 @@ struct mips_handle {
   CUtensorMap tmap_e;
   bool bound = false;
   // kernel geometry
-  int num_kchunks = 0, num_stages = 0;
+  int num_kchunks = 0, num_stages = 0, chunks_per_stage = 2;
   size_t smem_bytes = 0;
   // internal buffers
   void* ws = nullptr;
@@ -168,12 +169,22 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
   h->dtype = index_dtype;
   h->num_sms = prop.multiProcessorCount;
   h->num_kchunks = dim / kKChunk;
-  const int q_bytes = h->num_kchunks * kQChunkBytes;
-  int stages = (kMaxSmem - 1024 - kCtrlBytes - q_bytes) / kStageBytes;
+  // queries live in tensor memory (up to kMaxTsChunks K chunks); only a longer K tail needs shared memory
+  const int q_bytes = (h->num_kchunks > kMaxTsChunks ? h->num_kchunks - kMaxTsChunks : 0) * kQChunkBytes;
+  // Two pipeline stages, each as deep in K as fits: every stage hand-off (mbarrier round trip +
+  // tcgen05.commit) costs the MMA issuer ~200 cycles during which the tensor pipe drains, so the
+  // fewer, larger stages win (measured: 2 x 96 KiB stages beat 12 x 16 KiB by 20 % at dim 768).
+  int cps = ((kMaxSmem - 1024 - kCtrlBytes - q_bytes) / 2) / kChunkBytes;
+  if (const char* e = getenv("JSA_MIPS_CPS")) cps = atoi(e);   // tuning knob: K chunks per pipeline stage
+  if (cps < 1) cps = 1;
+  if (cps > h->num_kchunks) cps = h->num_kchunks;
+  const int stage_bytes = cps * kChunkBytes;
+  int stages = (kMaxSmem - 1024 - kCtrlBytes - q_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete h; return fail(nullptr, MIPS_EINVAL, "dim=%d leaves no room for the TMA pipeline", dim); }
   h->num_stages = stages;
-  h->smem_bytes = 1024 + q_bytes + static_cast<size_t>(stages) * kStageBytes + kCtrlBytes;
+  h->chunks_per_stage = cps;
+  h->smem_bytes = 1024 + q_bytes + static_cast<size_t>(stages) * stage_bytes + kCtrlBytes;
   cudaError_t e = configure_scan(h->smem_bytes);
   if (e != cudaSuccess) {
     delete h;
@@ -206,7 +217,7 @@ int mips_bind_index(mips_handle* h, const void* emb, int64_t n_local, int64_t ld
   h->id_stride = id_stride;
   h->bound = false;
   if (n_local > 0) {
-    int rc = encode_rows_map(h, &h->tmap_e, emb, n_local, ld, kTileM);
+    int rc = encode_rows_map(h, &h->tmap_e, emb, n_local, ld, kTileN);
     if (rc != MIPS_OK) return rc;
   }
   h->bound = true;
@@ -226,8 +237,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   h->last_launches = 0;
   if (!h->bound) return fail(h, MIPS_ENOTBOUND, "mips_bind_index has not been called");
   if (batch < 0 || k <= 0) return fail(h, MIPS_EINVAL, "batch=%d k=%d invalid", batch, k);
-  if (k > kMaxK) return fail(h, MIPS_EINVAL, "k=%d exceeds the fused top-k limit %d", k, kMaxK);
   if (k > h->n_local) return fail(h, MIPS_EKRANGE, "selected index k out of range (k=%d > n_local=%lld)", k, (long long)h->n_local);
+  if (k > kMaxK) return fail(h, MIPS_EINVAL, "k=%d exceeds the fused top-k limit %d", k, kMaxK);
   if (batch == 0) return MIPS_OK;
   if (!queries || !out_scores || !out_ids) return fail(h, MIPS_EINVAL, "NULL queries/outputs");
   if (q_dtype < 0 || q_dtype > 2) return fail(h, MIPS_EINVAL, "q_dtype=%d invalid", q_dtype);
@@ -261,15 +272,18 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   int rc = encode_rows_map(h, &tmap_q, qbuf, bpad, h->dim, kNQ);
   if (rc != MIPS_OK) return rc;
 
-  const int num_tiles = static_cast<int>((h->n_local + kTileM - 1) / kTileM);
+  const int num_tiles = static_cast<int>((h->n_local + kTileN - 1) / kTileN);
   const int grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
   ScanParams p;
   p.n_local = h->n_local;
   p.num_tiles = num_tiles;
   p.num_kchunks = h->num_kchunks;
   p.num_stages = h->num_stages;
+  p.chunks_per_stage = h->chunks_per_stage;
   p.k = k;
-  p.idesc = ptx::make_idesc_f16(kTileM, kNQ, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
+  p.idesc = ptx::make_idesc_f16(kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
+  p.dim = h->dim;
+  p.qbuf = qbuf;
   p.cand = reinterpret_cast<uint64_t*>(ws + w.cand_off);
   p.part_cnt = reinterpret_cast<int*>(ws + w.pk_off);
   p.id_base = h->id_base;
@@ -283,16 +297,20 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   // compacted in-stream and the select kernel takes the raw lists.  levels[] holds the tiles per CTA
   // of each pre-pass (the first is unseeded and one tile deep, so its lists hold <= 128 entries).
   const int tiles_per_cta = (num_tiles + grid - 1) / grid;
-  int levels[4];
+  int levels[6];
   int n_levels = 0;
-  if (tiles_per_cta >= 4 && !(h->dbg_flags & kDbgNoSeed)) {
+  if (tiles_per_cta >= 8 && !(h->dbg_flags & kDbgNoSeed)) {
+    const int64_t denom = static_cast<int64_t>(grid) * 150;   // target ~150 appended candidates per (CTA, query)
     int64_t need = tiles_per_cta;
-    int tmp[4];
+    int tmp[6];
     int nt = 0;
-    while (need > 1 && nt < 4) {
-      need = (need * k + static_cast<int64_t>(grid) * 150 - 1) / (static_cast<int64_t>(grid) * 150);
-      if (need < 1) need = 1;
-      tmp[nt++] = static_cast<int>(need);
+    while (nt < 6) {
+      int64_t nxt = (need * k + denom - 1) / denom;
+      if (nxt < 1) nxt = 1;
+      if (nxt >= need) break;
+      tmp[nt++] = static_cast<int>(nxt);
+      need = nxt;
+      if (nxt <= kEmit / kTileN) break;   // an unseeded pass this short leaves <= kEmit candidates per list
     }
     for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
   }
@@ -308,7 +326,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       pp.num_tiles = levels[lv] * grid < num_tiles ? levels[lv] * grid : num_tiles;
       pp.stats = nullptr;
       CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, pp, grid, h->smem_bytes, st));
-      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, kNQ, k, 0, 1, seed_scores, seed_ids, st));
+      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.batch, k, 0, 1, seed_scores, seed_ids, st));
       h->last_launches += 2;
       p.seed = seed_scores;
     }

@@ -7,31 +7,37 @@
 namespace mips {
 
 // ---- compile-time geometry of the fused scan kernel ----
-constexpr int kTileM = 128;      // passages per tile   (UMMA M, one TMEM lane per passage)
-constexpr int kNQ = 64;          // query columns/pass  (UMMA N, one TMEM column per query)
+// D[query, passage] = Q[query, :] . P[passage, :]   with tcgen05.mma M=128 (queries), N=64 (passages)
+constexpr int kNQ = 128;         // queries per pass (UMMA M): one TMEM lane / one epilogue thread per query
+constexpr int kTileN = 64;       // passages per tile (UMMA N): one fp32 TMEM column per passage
 constexpr int kKChunk = 64;      // elements per K chunk: 64 x 2 B = one 128-byte swizzle row
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
-constexpr int kStageBytes = kTileM * kKChunk * 2;   // 16 KiB passage chunk per pipeline stage
-constexpr int kQChunkBytes = kNQ * kKChunk * 2;     // 8 KiB query chunk (resident for the whole kernel)
-constexpr int kMaxStages = 8;
+constexpr int kChunkBytes = kTileN * kKChunk * 2;                 // 8 KiB: [64 passages x 64 el], SWIZZLE_128B
+constexpr int kQChunkBytes = kNQ * kKChunk * 2;                   // 16 KiB: [128 queries x 64 el] (smem-resident K tail)
+constexpr int kMaxStages = 12;
+constexpr int kTmemCols = 512;   // whole TMEM: queries (A operand) + two accumulator buffers
+constexpr int kAccCol0 = kTmemCols - 2 * kTileN;                  // accumulators live in the last 128 columns
+constexpr int kMaxTsChunks = kAccCol0 / (kKChunk / 2);            // 12 K chunks (768 dims) of the queries fit in TMEM
 constexpr int kCap = 512;        // candidate slots per (CTA, query) in the L2-resident candidate lists
-constexpr int kSortE = kCap / 32;  // keys per lane in the warp bitonic sort
+constexpr int kSortE = kCap / 32;  // keys per lane when a warp compacts one list
 constexpr int kEmit = 256;       // a CTA hands at most this many candidates per query to the select kernel
 constexpr int kMaxK = 128;       // largest fused top-k
 constexpr int kMaxDim = 1024;
 constexpr int kScanThreads = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue/select
-constexpr int kCtrlBytes = 1280;   // barriers + thresholds + counters
+constexpr int kCtrlBytes = 1024;   // barriers + TMEM base pointer
 constexpr int kMaxSmem = 232448;   // 227 KiB opt-in dynamic shared memory per CTA on sm_100
-constexpr int kTmemCols = 2 * kNQ; // double-buffered fp32 accumulators
 
 struct ScanParams {
   int64_t n_local;       // rows in this shard
-  int num_tiles;         // ceil(n_local / kTileM)
+  int num_tiles;         // tiles (of kTileN passages) this launch scans: tiles [0, num_tiles)
   int num_kchunks;       // dim / 64
   int num_stages;        // pipeline depth that fits next to the resident queries
+  int chunks_per_stage;  // K chunks (8 KiB each) one pipeline stage carries
   int k;                 // top-k (<= kMaxK)
-  int batch;             // valid query columns in this pass (<= kNQ)
+  int batch;             // valid queries in this pass (<= kNQ)
   int q_row0;            // first row of this pass in the prepared query buffer
+  int dim;               // embedding dimension
+  const void* qbuf;      // prepared queries [batch_pad, dim] in the index dtype (row-major, zero padded)
   uint32_t idesc;        // tcgen05 instruction descriptor (dtype dependent)
   uint64_t* cand;        // [grid][kNQ][kCap] packed (orderable score << 32 | ~row) keys
   int* part_cnt;         // [grid][kNQ] number of candidates each CTA leaves at the head of its lists
@@ -42,9 +48,9 @@ struct ScanParams {
 };
 
 constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
-constexpr int kDbgNoMma = 2;
-constexpr int kDbgNoSeed = 4;
-constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)    // disable the sampled pre-pass (thresholds start at -inf)     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
+constexpr int kDbgNoMma = 2;     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
+constexpr int kDbgNoSeed = 4;    // disable the sampled pre-passes (thresholds start at -inf)
+constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };
 

@@ -3,15 +3,20 @@
 // Replaces  scores = torch.matmul(allqueries.half(), self.embeddings); torch.topk(scores, k)
 // (reference src/index.py:118-119) without ever writing the [batch, n_local] score matrix.
 //
-// One persistent CTA per SM.  Passage rows (K-major, [n_local, dim]) are streamed from HBM exactly
-// once per query pass by TMA into a multi-stage shared-memory ring; the <=64 queries of the pass
-// stay resident in shared memory as the B operand.  Per 128-passage tile the MMA warp issues
-// dim/16 tcgen05.mma (M=128 passages x N=64 queries x K=16) into one of two TMEM accumulator
-// buffers; four epilogue warps read the accumulators back (tcgen05.ld, one passage per thread),
-// compare against per-query running thresholds held in shared memory and append the rare
-// survivors to small L2-resident candidate lists.  When a list nears capacity one warp bitonic-
-// sorts it in registers, keeps the best k and raises the query's threshold.  At the end each CTA
-// emits its sorted top-k per query; merge.cu reduces the per-CTA lists.
+// Query-stationary design, one persistent CTA per SM:
+//  * the <=128 queries of a pass are the A operand and live in TENSOR MEMORY for the whole kernel
+//    (128 lanes x dim/2 columns; up to 768 dims — a longer K tail stays in shared memory);
+//  * passage rows (K-major, [n_local, dim]) are streamed from HBM exactly once per pass by TMA into
+//    a shared-memory ring and are the B operand; each byte of the index is read from shared memory
+//    once (the smem->tensor-core operand path, ~64 B/clk/SM, is the second-tightest resource);
+//  * per 64-passage tile the MMA warp issues dim/16 tcgen05.mma (M=128 queries x N=64 passages x
+//    K=16) into one of two TMEM accumulator buffers;
+//  * four epilogue warps own 32 queries each — one thread per query: tcgen05.ld brings the 64 scores
+//    of the tile, each is compared with the query's running threshold (a register), and the rare
+//    survivors are appended to the query's candidate list (L2-resident, per CTA).  No atomics, no
+//    cross-warp synchronisation.  When a list nears capacity its warp cuts it back to the best k
+//    (exact bisection select, no sort) and raises the threshold.
+// The per-CTA lists are reduced by select_topk_kernel (merge.cu).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue/select (TMEM lane quarter = warp_id % 4).
@@ -48,10 +53,9 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
 }
 
 // Keeps exactly the k best (largest-key) of the c > k candidates of one list, in place and
-// unsorted, and publishes the k-th best as the query's new threshold.  Keys are unique (they
-// embed the row), so "key >= k-th largest key" selects exactly k entries.  Whole warp.
-__device__ __forceinline__ void compact_list(uint64_t* __restrict__ list, int c, int k, int lane,
-                                             uint64_t* thrkey_s, float* thr_s, int* cnt_s, int q) {
+// unsorted, and returns the k-th best key (the list owner's new threshold).  Keys are unique (they
+// embed the row), so "key >= k-th largest key" selects exactly k entries.  Whole warp, converged.
+__device__ __noinline__ uint64_t compact_list(uint64_t* __restrict__ list, int c, int k, int lane) {
   uint64_t key[kSortE];
   uint32_t hi[kSortE];
   const ulonglong2* src = reinterpret_cast<const ulonglong2*>(list + lane * kSortE);
@@ -104,18 +108,27 @@ __device__ __forceinline__ void compact_list(uint64_t* __restrict__ list, int c,
 #pragma unroll
   for (int e = 0; e < kSortE; ++e)
     if (key[e] >= thrkey) list[pos++] = key[e];
-  if (lane == 0) {
-    thrkey_s[q] = thrkey;
-    thr_s[q] = ord_to_f32(t_hi);
-    cnt_s[q] = k;
+  __syncwarp();
+  return thrkey;
+}
+
+// r[c] for a runtime c in [0, 64): registers cannot be indexed dynamically, so pick through a
+// 6-level select tree (63 selects; only executed for the rare survivors).
+__device__ __forceinline__ uint32_t pick64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int c) {
+  uint32_t t[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) t[i] = (c & 32) ? r1[i] : r0[i];
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = (c & w) ? t[i + w] : t[i];
   }
+  return t[0];
 }
 
 // ------------------------------------------------------------------------------------------------
 // The scan kernel
 // ------------------------------------------------------------------------------------------------
-#define SCORE(q) __uint_as_float((q) < 32 ? r0[(q)&31] : r1[(q)&31])
-
 __global__ void __launch_bounds__(kScanThreads, 1)
 mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_q,
                  const ScanParams p) {
@@ -124,16 +137,18 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw_addr);
 
-  const int nk = p.num_kchunks;
+  const int nk = p.num_kchunks;                               // K chunks of 64 elements
+  const int nk_ts = nk < kMaxTsChunks ? nk : kMaxTsChunks;    // ... of which the queries sit in TMEM
+  const int nk_ss = nk - nk_ts;                               // ... and in shared memory (dim > 768)
   const int S = p.num_stages;
-  const uint32_t q_smem = base;                                // nk chunks of [64 q x 64 el]
-  const uint32_t st_smem = base + nk * kQChunkBytes;           // S stages of [128 p x 64 el]
-  uint8_t* ctrl = smem + nk * kQChunkBytes + S * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);          // full[8] empty[8] tfull[2] tempty[2] qfull
-  uint64_t* thrkey_s = bars + 24;                              // [64]
-  float* thr_s = reinterpret_cast<float*>(thrkey_s + kNQ);     // [64]
-  int* cnt_s = reinterpret_cast<int*>(thr_s + kNQ);            // [64]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(cnt_s + kNQ);
+  const int cps = p.chunks_per_stage;                            // K chunks one pipeline stage carries
+  const int stage_bytes = cps * kChunkBytes;
+  const int stages_per_tile = (nk + cps - 1) / cps;
+  const uint32_t q_smem = base;                               // nk_ss chunks of [128 q x 64 el]
+  const uint32_t st_smem = base + nk_ss * kQChunkBytes;       // S stages of 2 x [64 p x 64 el]
+  uint8_t* ctrl = smem + nk_ss * kQChunkBytes + S * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);         // full[12] empty[12] tfull[2] tempty[2] qfull
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 32);
 
   const uint32_t bar_full = ptx::smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
@@ -147,7 +162,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   // ---------------- one-time setup ----------------
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_e);
-    ptx::prefetch_tensormap(&tmap_q);
+    if (nk_ss > 0) ptx::prefetch_tensormap(&tmap_q);
     for (int s = 0; s < kMaxStages; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
       ptx::mbar_init(bar_empty + 8 * s, 1);
@@ -158,16 +173,6 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     }
     ptx::mbar_init(bar_qfull, 1);
     ptx::fence_barrier_init();
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kNQ) {
-    const int q = threadIdx.x - 64;
-    const bool live = q < p.batch;  // padded query columns never pass the filter
-    // initial threshold: the k-th best score of the sampled pre-pass when there is one (valid lower
-    // bound of the final k-th score), else -inf
-    const float seed = p.seed ? p.seed[static_cast<size_t>(q) * p.k + (p.k - 1)] : -INFINITY;
-    thr_s[q] = live ? seed : INFINITY;
-    thrkey_s[q] = live ? (static_cast<uint64_t>(f32_to_ord(seed)) << 32) : ~0ull;
-    cnt_s[q] = 0;
   }
   if (warp == 1) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_s), kTmemCols);
@@ -184,7 +189,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   const bool want_stats = p.stats != nullptr;
   unsigned long long* my_stats = want_stats ? p.stats + static_cast<size_t>(blockIdx.x) * kNumStats : nullptr;
   const long long t_start = clock64();
-  long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, st_e = 0;
+  long long st_a = 0, st_b = 0, st_c = 0, st_d = 0;
   int st_m = 0, st_n = 0;
 
   // Roles run warp-uniformly (all 32 lanes take the same path and wait on the same barriers);
@@ -192,23 +197,27 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   // addresses and descriptors in uniform registers and the issue loops short.
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(bar_qfull, nk * kQChunkBytes);
-      for (int kc = 0; kc < nk; ++kc)
-        ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, kc * kKChunk, p.q_row0, ptx::kEvictLast);
+    if (nk_ss > 0 && ptx::elect_one()) {  // K tail of the queries: resident in shared memory
+      ptx::mbar_arrive_expect_tx(bar_qfull, nk_ss * kQChunkBytes);
+      for (int kc = 0; kc < nk_ss; ++kc)
+        ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, (nk_ts + kc) * kKChunk, p.q_row0,
+                         ptx::kEvictLast);
     }
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
     for (int t = first_tile; t < p.num_tiles; t += tile_step) {
-      for (int kc = 0; kc < nk; ++kc) {
+      for (int si = 0; si < stages_per_tile; ++si) {
         const long long w0 = want_stats ? clock64() : 0;
         ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
         if (want_stats) st_a += clock64() - w0;
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-          ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * kStageBytes, kc * kKChunk, t * kTileM,
-                           ptx::kEvictFirst);
+          const int kc0 = si * cps;
+          const int nch = nk - kc0 < cps ? nk - kc0 : cps;
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, nch * kChunkBytes);
+          for (int c = 0; c < nch; ++c)
+            ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * stage_bytes + c * kChunkBytes,
+                             (kc0 + c) * kKChunk, t * kTileN, ptx::kEvictFirst);
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -217,7 +226,9 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     if (want_stats && lane == 0) my_stats[kStProdWait] = st_a;
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    ptx::mbar_wait(bar_qfull, 0);
+    if (nk_ss > 0) ptx::mbar_wait(bar_qfull, 0);
+    ptx::named_bar_sync(2, 160);  // the epilogue warps have written the queries to TMEM
+    ptx::tc_fence_after();
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -228,26 +239,39 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       ptx::mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
       if (want_stats) st_b += clock64() - w0;
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * kNQ;
-      for (int kc = 0; kc < nk; ++kc) {
+      const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kTileN;
+      for (int si = 0; si < stages_per_tile; ++si) {
         w0 = want_stats ? clock64() : 0;
         ptx::mbar_wait(bar_full + 8 * stage, phase);
         if (want_stats) st_a += clock64() - w0;
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
+          const bool last = si == stages_per_tile - 1;
           if (no_mma) {
             ptx::mbar_arrive(bar_empty + 8 * stage);
-            if (kc == nk - 1) ptx::mbar_arrive(bar_tfull + 8 * buf);
+            if (last) ptx::mbar_arrive(bar_tfull + 8 * buf);
           } else {
-            // K-major SWIZZLE_128B descriptors; advancing K by 16 elements = +32 bytes (= +2 in the
-            // 16-byte-granular start-address field) inside the 128-byte swizzle row
-            const uint64_t da = ptx::make_kmajor_sw128_desc(st_smem + stage * kStageBytes);
-            const uint64_t db = ptx::make_kmajor_sw128_desc(q_smem + kc * kQChunkBytes);
+            const int kc0 = si * cps;
+            const int nch = nk - kc0 < cps ? nk - kc0 : cps;
+            for (int c = 0; c < nch; ++c) {
+              const int kc = kc0 + c;
+              // B: 64 passages x 64 el, K-major SWIZZLE_128B; +32 B (= +2 in the descriptor) per K=16 step
+              const uint64_t db = ptx::make_kmajor_sw128_desc(st_smem + stage * stage_bytes + c * kChunkBytes);
+              if (kc < nk_ts) {
+                // A from TMEM: 8 columns (16 packed 16-bit values per lane) per K=16 step
+                const uint32_t a_tmem = tmem_base + kc * (kKChunk / 2);
 #pragma unroll
-            for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
-              ptx::umma_f16(d_tmem, da + 2 * k4, db + 2 * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+                for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
+                  ptx::umma_f16_ts(d_tmem, a_tmem + 8 * k4, db + 2 * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+              } else {
+                const uint64_t da = ptx::make_kmajor_sw128_desc(q_smem + (kc - nk_ts) * kQChunkBytes);
+#pragma unroll
+                for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
+                  ptx::umma_f16(d_tmem, da + 2 * k4, db + 2 * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+              }
+            }
             ptx::umma_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs retire
-            if (kc == nk - 1) ptx::umma_commit(bar_tfull + 8 * buf);
+            if (last) ptx::umma_commit(bar_tfull + 8 * buf);
           }
         }
         __syncwarp();
@@ -257,12 +281,40 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     if (want_stats && lane == 0) { my_stats[kStMmaWaitFull] = st_a; my_stats[kStMmaWaitTmem] = st_b; }
   } else {
     // =========================== epilogue / select ===========================
-    const int ew = warp - 2;        // 0..3: which 16 queries this warp compacts
-    const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int quarter = warp & 3;           // TMEM lanes [32*quarter, +32) are accessible to this warp
+    const int ql = quarter * 32 + lane;     // my query (TMEM lane) within the pass
+    const bool live = ql < p.batch;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint64_t* my_cand = p.cand + static_cast<size_t>(blockIdx.x) * kNQ * kCap;
+    uint64_t* warp_lists = p.cand + (static_cast<size_t>(blockIdx.x) * kNQ + quarter * 32) * kCap;
+    uint64_t* my_list = warp_lists + static_cast<size_t>(lane) * kCap;
     const bool no_select = (p.flags & kDbgNoSelect) != 0;
-    const uint32_t cnt_addr = ptx::smem_u32(cnt_s);
+
+    // ---- queries -> TMEM (A operand, K-major: column c of a chunk holds elements 2c, 2c+1) ----
+    {
+      const uint32_t* qrow = reinterpret_cast<const uint32_t*>(
+          static_cast<const uint16_t*>(p.qbuf) + static_cast<size_t>(p.q_row0 + ql) * p.dim);
+      for (int kc = 0; kc < nk_ts; ++kc) {
+        uint32_t w[32];
+        const uint4* src = reinterpret_cast<const uint4*>(qrow + kc * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = src[i];
+          w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        ptx::tmem_st_32x32b_x32(t_lane + kc * 32, w);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::named_bar_sync(2, 160);
+    }
+
+    // ---- per-query state lives in registers ----
+    // initial threshold: the k-th best score of the sampled pre-pass when there is one (a valid
+    // lower bound of the final k-th score), else -inf; dead (padding) queries never pass
+    const float seed = p.seed ? p.seed[static_cast<size_t>(ql) * p.k + (p.k - 1)] : -INFINITY;
+    float thr = live ? seed : INFINITY;
+    uint64_t thrkey = live ? (static_cast<uint64_t>(f32_to_ord(seed)) << 32) : ~0ull;
+    int cnt = 0;
 
     int it = 0;
     for (int t = first_tile; t < p.num_tiles; t += tile_step, ++it) {
@@ -272,128 +324,76 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       if (want_stats) { const long long w1 = clock64(); st_a += w1 - w0; w0 = w1; }
       ptx::tc_fence_after();
       uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32b_x32(t_lane + buf * kNQ, r0);
-      ptx::tmem_ld_32x32b_x32(t_lane + buf * kNQ + 32, r1);
+      const uint32_t acc = t_lane + kAccCol0 + buf * kTileN;
+      ptx::tmem_ld_32x32b_x32(acc, r0);
+      ptx::tmem_ld_32x32b_x32(acc + 32, r1);
       ptx::tmem_ld_wait();
-      if (want_stats) { const long long w1 = clock64(); st_d += w1 - w0; w0 = w1; }
-      if (no_select) {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-        continue;
-      }
-
-      const int64_t row = static_cast<int64_t>(t) * kTileM + quarter * 32 + lane;
-      const bool valid = row < p.n_local;
-      const uint32_t row32 = static_cast<uint32_t>(row);
-      bool need_compact = false;
-
-      // ---- select ----
-      // A (static, ~2 instructions per score): per-thread bitmask of the queries whose running
-      //   threshold this passage reaches, OR-reduced over the warp into the set of non-empty queries.
-      // B (dynamic, compact code, 4 queries per round): the score column of each non-empty query is
-      //   re-read from TMEM (tcgen05.ld x1 takes a runtime column, registers cannot be indexed
-      //   dynamically), the exact 64-bit key test decides score ties by row, lanes 0..3 reserve
-      //   slots with ONE shared-memory atomic instruction, and the survivors are stored.
-      // Keeping B out of the unrolled code keeps the per-tile loop inside the instruction cache.
-      const float4* thr4 = reinterpret_cast<const float4*>(thr_s);
-      const uint32_t lt_mask = (1u << lane) - 1u;
-      uint32_t pm0 = 0, pm1 = 0;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 th = thr4[g];
-        if (__uint_as_float(r0[4 * g + 0]) >= th.x) pm0 |= 1u << (4 * g + 0);
-        if (__uint_as_float(r0[4 * g + 1]) >= th.y) pm0 |= 1u << (4 * g + 1);
-        if (__uint_as_float(r0[4 * g + 2]) >= th.z) pm0 |= 1u << (4 * g + 2);
-        if (__uint_as_float(r0[4 * g + 3]) >= th.w) pm0 |= 1u << (4 * g + 3);
-      }
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 th = thr4[8 + g];
-        if (__uint_as_float(r1[4 * g + 0]) >= th.x) pm1 |= 1u << (4 * g + 0);
-        if (__uint_as_float(r1[4 * g + 1]) >= th.y) pm1 |= 1u << (4 * g + 1);
-        if (__uint_as_float(r1[4 * g + 2]) >= th.z) pm1 |= 1u << (4 * g + 2);
-        if (__uint_as_float(r1[4 * g + 3]) >= th.w) pm1 |= 1u << (4 * g + 3);
-      }
-      if (!valid) pm0 = pm1 = 0u;
-      uint32_t ne0 = __reduce_or_sync(0xffffffffu, pm0);
-      uint32_t ne1 = __reduce_or_sync(0xffffffffu, pm1);
-#pragma unroll 1
-      while ((ne0 | ne1) != 0u) {  // warp-uniform
-        int qs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (ne0 != 0u) { qs[u] = __ffs(ne0) - 1; ne0 &= ne0 - 1u; }
-          else if (ne1 != 0u) { qs[u] = 32 + __ffs(ne1) - 1; ne1 &= ne1 - 1u; }
-          else qs[u] = -1;
-        }
-        uint32_t sv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) sv[u] = ptx::tmem_ld_32x32b_x1(t_lane + buf * kNQ + (qs[u] < 0 ? 0 : qs[u]));
-        ptx::tmem_ld_wait();
-        uint64_t kk[4];
-        uint32_t m[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = qs[u] < 0 ? 0 : qs[u];
-          const uint32_t bits = q < 32 ? pm0 : pm1;
-          const bool mine = qs[u] >= 0 && ((bits >> (q & 31)) & 1u);
-          kk[u] = make_key(__uint_as_float(sv[u]), row32);
-          m[u] = __ballot_sync(0xffffffffu, mine && kk[u] > thrkey_s[q]);
-        }
-        const uint32_t mym = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : lane == 3 ? m[3] : 0u;
-        const int myq = lane == 0 ? qs[0] : lane == 1 ? qs[1] : lane == 2 ? qs[2] : qs[3];
-        int old = 0;
-        if (mym != 0u) old = atomicAdd(&cnt_s[myq], __popc(mym));  // lanes 0..3, distinct addresses
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int basep = __shfl_sync(0xffffffffu, old, u);
-          if ((m[u] >> lane) & 1u) {
-            const int pos = basep + __popc(m[u] & lt_mask);
-            my_cand[qs[u] * kCap + pos] = kk[u];
-            need_compact |= pos >= kCap - kTileM;
-            ++st_n;
-          }
-        }
-      }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);  // TMEM buffer may be overwritten now
-      // all appends of this tile are done; lists that could overflow during the next tile are
-      // compacted (one barrier with an OR-reduction tells every warp whether any list needs it)
-      if (want_stats) { const long long w1 = clock64(); st_b += w1 - w0; w0 = w1; }
-      const bool do_compact = ptx::named_bar_red_or(1, 128, need_compact);
-      if (want_stats) { const long long w1 = clock64(); st_e += w1 - w0; w0 = w1; }
-      if (do_compact) {
-#pragma unroll 1
-        for (int i = 0; i < kNQ / 4; ++i) {
-          const int q = ew * (kNQ / 4) + i;
-          const int c = cnt_s[q];
-          if (c > kCap - kTileM) {
-            compact_list(my_cand + q * kCap, c, p.k, lane, thrkey_s, thr_s, cnt_s, q);
-            ++st_m;
-          }
-        }
-        ptx::named_bar_sync(1, 128);
-        if (want_stats) st_c += clock64() - w0;
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);  // the 64 scores are in registers now
+      if (want_stats) { const long long w1 = clock64(); st_d += w1 - w0; w0 = w1; }
+      if (no_select) continue;
+
+      // ---- filter: bitmask of the passages of this tile that reach my query's threshold ----
+      uint32_t pm0 = 0, pm1 = 0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (__uint_as_float(r0[c]) >= thr) pm0 |= 1u << c;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (__uint_as_float(r1[c]) >= thr) pm1 |= 1u << c;
+      const int64_t row0 = static_cast<int64_t>(t) * kTileN;
+      const int64_t nvalid = p.n_local - row0;  // rows past the end are zero-filled by TMA: mask them
+      if (nvalid < kTileN) {
+        const uint64_t vm = (1ull << nvalid) - 1ull;
+        pm0 &= static_cast<uint32_t>(vm);
+        pm1 &= static_cast<uint32_t>(vm >> 32);
       }
+      // ---- rare path: append the survivors (exact key test decides score ties by row) ----
+      while ((pm0 | pm1) != 0u) {
+        int c;
+        if (pm0 != 0u) { c = __ffs(pm0) - 1; pm0 &= pm0 - 1u; }
+        else { c = 32 + __ffs(pm1) - 1; pm1 &= pm1 - 1u; }
+        const float s = __uint_as_float(pick64(r0, r1, c));
+        const uint64_t kk = make_key(s, static_cast<uint32_t>(row0) + c);
+        if (kk > thrkey) {
+          my_list[cnt++] = kk;
+          ++st_n;
+        }
+      }
+      __syncwarp();
+      if (want_stats) { const long long w1 = clock64(); st_b += w1 - w0; w0 = w1; }
+      // ---- lists that could overflow during the next tile are cut back to their best k ----
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - kTileN);
+      while (need != 0u) {  // warp-uniform
+        const int l = __ffs(need) - 1;
+        need &= need - 1u;
+        const int c = __shfl_sync(0xffffffffu, cnt, l);
+        const uint64_t nk_key = compact_list(warp_lists + static_cast<size_t>(l) * kCap, c, p.k, lane);
+        if (lane == l) {
+          thrkey = nk_key;
+          thr = ord_to_f32(static_cast<uint32_t>(nk_key >> 32));
+          cnt = p.k;
+        }
+        ++st_m;
+      }
+      if (want_stats) st_c += clock64() - w0;
     }
 
     // ---------------- final: publish this CTA's candidate counts ----------------
     // The candidate lists stay where they are (L2-resident workspace); the select kernel reads
     // them directly.  Only lists longer than kEmit are first cut down to their best k.
     if (!no_select) {
-#pragma unroll 1
-      for (int i = 0; i < kNQ / 4; ++i) {
-        const int q = ew * (kNQ / 4) + i;
-        int c = cnt_s[q];
-        if (c > kEmit) {
-          compact_list(my_cand + q * kCap, c, p.k, lane, thrkey_s, thr_s, cnt_s, q);
-          c = p.k;
-          ++st_m;
-        }
-        if (lane == 0) p.part_cnt[static_cast<size_t>(blockIdx.x) * kNQ + q] = c;
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > kEmit);
+      while (need != 0u) {
+        const int l = __ffs(need) - 1;
+        need &= need - 1u;
+        const int c = __shfl_sync(0xffffffffu, cnt, l);
+        compact_list(warp_lists + static_cast<size_t>(l) * kCap, c, p.k, lane);
+        if (lane == l) cnt = p.k;
+        ++st_m;
       }
+      p.part_cnt[static_cast<size_t>(blockIdx.x) * kNQ + ql] = cnt;
     }
     if (want_stats && lane == 0) {
       atomicAdd(&my_stats[kStEpiWaitTmem], static_cast<unsigned long long>(st_a));
@@ -401,7 +401,6 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       atomicAdd(&my_stats[kStEpiCompact], static_cast<unsigned long long>(st_c));
       atomicAdd(&my_stats[kStNumCompact], static_cast<unsigned long long>(st_m));
       atomicAdd(&my_stats[kStEpiLd], static_cast<unsigned long long>(st_d));
-      atomicAdd(&my_stats[kStEpiBar], static_cast<unsigned long long>(st_e));
     }
     if (want_stats) atomicAdd(&my_stats[kStNumAppend], static_cast<unsigned long long>(st_n));
   }
@@ -415,7 +414,6 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
-#undef SCORE
 
 cudaError_t configure_scan(size_t smem_bytes) {
   return cudaFuncSetAttribute(mips_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

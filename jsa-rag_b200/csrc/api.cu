@@ -321,6 +321,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     p.batch = batch - q0 < kNQ ? batch - q0 : kNQ;
     p.q_row0 = q0;
     p.seed = nullptr;
+    p.m64 = (p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
+    p.idesc = ptx::make_idesc_f16(p.m64 ? 64 : kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
     for (int lv = 0; lv < n_levels; ++lv) {
       ScanParams pp = p;
       pp.num_tiles = levels[lv] * grid < num_tiles ? levels[lv] * grid : num_tiles;

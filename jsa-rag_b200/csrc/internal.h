@@ -35,6 +35,7 @@ struct ScanParams {
   int chunks_per_stage;  // K chunks (8 KiB each) one pipeline stage carries
   int k;                 // top-k (<= kMaxK)
   int batch;             // valid queries in this pass (<= kNQ)
+  int m64;               // 1: UMMA M=64 (batch <= 64), 0: UMMA M=128
   int q_row0;            // first row of this pass in the prepared query buffer
   int dim;               // embedding dimension
   const void* qbuf;      // prepared queries [batch_pad, dim] in the index dtype (row-major, zero padded)
@@ -50,6 +51,7 @@ struct ScanParams {
 constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
 constexpr int kDbgNoMma = 2;     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
 constexpr int kDbgNoSeed = 4;    // disable the sampled pre-passes (thresholds start at -inf)
+constexpr int kDbgForceM128 = 16; // always use UMMA M=128 (A/B test of the M=64 small-batch mode)
 constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };

@@ -281,12 +281,16 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     if (want_stats && lane == 0) { my_stats[kStMmaWaitFull] = st_a; my_stats[kStMmaWaitTmem] = st_b; }
   } else {
     // =========================== epilogue / select ===========================
+    // UMMA M=128: query m sits in TMEM lane m.  UMMA M=64 (passes of <= 64 queries; half the tensor
+    // work and power): query m sits in lane 32*(m/16) + m%16, i.e. lanes 0..15 of every lane quarter.
     const int quarter = warp & 3;           // TMEM lanes [32*quarter, +32) are accessible to this warp
-    const int ql = quarter * 32 + lane;     // my query (TMEM lane) within the pass
-    const bool live = ql < p.batch;
+    const int per_warp = p.m64 ? 16 : 32;   // queries owned by this warp
+    const bool lane_ok = lane < per_warp;
+    const int ql = quarter * per_warp + (lane_ok ? lane : 0);   // my query within the pass
+    const bool live = lane_ok && ql < p.batch;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint64_t* warp_lists = p.cand + (static_cast<size_t>(blockIdx.x) * kNQ + quarter * 32) * kCap;
-    uint64_t* my_list = warp_lists + static_cast<size_t>(lane) * kCap;
+    uint64_t* warp_lists = p.cand + (static_cast<size_t>(blockIdx.x) * kNQ + quarter * per_warp) * kCap;
+    uint64_t* my_list = warp_lists + static_cast<size_t>(lane_ok ? lane : 0) * kCap;
     const bool no_select = (p.flags & kDbgNoSelect) != 0;
 
     // ---- queries -> TMEM (A operand, K-major: column c of a chunk holds elements 2c, 2c+1) ----
@@ -393,7 +397,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
         if (lane == l) cnt = p.k;
         ++st_m;
       }
-      p.part_cnt[static_cast<size_t>(blockIdx.x) * kNQ + ql] = cnt;
+      if (lane_ok) p.part_cnt[static_cast<size_t>(blockIdx.x) * kNQ + ql] = cnt;
     }
     if (want_stats && lane == 0) {
       atomicAdd(&my_stats[kStEpiWaitTmem], static_cast<unsigned long long>(st_a));

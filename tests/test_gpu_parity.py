@@ -250,7 +250,7 @@ def _properties(eng, dev, n, b, k, seed):
     assert all(len(set(r.tolist())) == k for r in i.cpu()), "duplicate ids"
     # returned scores are the true inner products of the returned rows
     got = torch.einsum("bd,bkd->bk", q.half().float(), e[i].float())
-    assert float((s - got).abs().max()) <= 2e-6 + 2e-6 * float(got.abs().max())
+    assert float((s - got).abs().max()) <= 2e-5 * max(1.0, float(got.abs().max()))   # fp32 summation order only
     # no row of a random 2M-row sample beats the k-th returned score (completeness of the scan)
     samp = torch.randint(0, n, (min(n, 2_000_000),), device=dev)
     for a in range(0, samp.numel(), 1 << 19):

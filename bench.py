@@ -176,6 +176,7 @@ def run_b200(args):
     index.init_embeddings([None] * 0, dim=args.dim)   # doc_map is not exercised by the tensor-level path
     index._store = torch.empty(n_loc, args.dim, dtype=tdtype, device=dev)
     index._set_sharding("round_robin")
+    index.equal_batch = True   # every rank contributes batch/N queries
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     for a in range(0, n_loc, 1 << 20):
         c = torch.randn(min(1 << 20, n_loc - a), args.dim, generator=g, device=dev)

@@ -59,27 +59,37 @@ def varsize_all_gather(x: torch.Tensor, sizes: Sequence[int] = None) -> torch.Te
         pad = x.new_zeros((max_size - x.size(0),) + tuple(x.shape[1:]))
         x = torch.cat((x, pad), dim=0)
     x = x.contiguous()
-    out = [torch.empty_like(x) for _ in sizes]
-    dist.all_gather(out, x)
-    return torch.cat([t[:n] for t, n in zip(out, sizes)], dim=0)
+    out = torch.empty((len(sizes),) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    _all_gather_into(out, x)
+    if all(n == max_size for n in sizes):
+        return out.view((len(sizes) * max_size,) + tuple(x.shape[1:]))
+    return torch.cat([out[r, :n] for r, n in enumerate(sizes)], dim=0)
+
+
+def _all_gather_into(out: torch.Tensor, x: torch.Tensor) -> None:
+    """dist.all_gather_into_tensor where the backend has it (NCCL), list all_gather otherwise (gloo)."""
+    try:
+        dist.all_gather_into_tensor(out, x)
+    except (RuntimeError, NotImplementedError):
+        parts = list(out.view(get_world_size(), *x.shape).unbind(0))
+        dist.all_gather(parts, x)
 
 
 @torch.no_grad()
 def all_gather_candidates(scores: torch.Tensor, ids: torch.Tensor):
-    """ONE all-gather of the packed per-rank result: scores fp32 [B,k] + ids int64 [B,k] ->
-    ([W,B,k] fp32, [W,B,k] int64).  12*B*k bytes per rank (77 KB at B=64, k=100)."""
+    """The one exchange step of the search: every rank contributes its local top-k
+    (fp32 scores [B,k], int64 global ids [B,k]; 12*B*k bytes per rank — 77 KB at B=64, k=100) and
+    receives all of them as ([W,B,k] fp32, [W,B,k] int64), laid out for the device merge: two
+    all_gather_into_tensor calls back to back (no packing kernels, no host sync)."""
     w = get_world_size()
     if w == 1:
         return scores.unsqueeze(0), ids.unsqueeze(0)
     b, k = scores.shape
-    packed = torch.empty((3, b, k), dtype=torch.int32, device=scores.device)
-    packed[0] = scores.contiguous().view(torch.int32)
-    packed[1:] = ids.contiguous().view(torch.int32).view(b, k, 2).permute(2, 0, 1)
-    out = [torch.empty_like(packed) for _ in range(w)]
-    dist.all_gather(out, packed)
-    allp = torch.stack(out, dim=0)  # [W, 3, B, k]
-    g_scores = allp[:, 0].contiguous().view(torch.float32)
-    g_ids = allp[:, 1:].permute(0, 2, 3, 1).contiguous().view(torch.int64).view(w, b, k)
+    scores, ids = scores.contiguous(), ids.contiguous()
+    g_scores = torch.empty((w, b, k), dtype=scores.dtype, device=scores.device)
+    g_ids = torch.empty((w, b, k), dtype=ids.dtype, device=ids.device)
+    _all_gather_into(g_scores, scores)
+    _all_gather_into(g_ids, ids)
     return g_scores, g_ids
 
 

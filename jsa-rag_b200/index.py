@@ -44,6 +44,10 @@ class B200Index(object):
         self._id_base, self._id_stride = 0, 1
         self._sharding = "round_robin"
         self.round_scores_to_index_dtype = True  # reference returns fp16-rounded scores (src/index.py:118,153)
+        # True: every rank always passes the same number of queries (fixed per-GPU batch, as in the
+        # reference's training loop; evaluate.py:49-54 pads iterators to keep ranks in step) -> the size
+        # exchange (a collective + a host sync, src/index.py:129-130) is skipped
+        self.equal_batch = False
         self.last_search_stats = {}
 
     # ------------------------------------------------------------------ storage
@@ -194,7 +198,7 @@ class B200Index(object):
                 dev = queries.device
                 return torch.empty(0, topk, device=dev), torch.empty(0, topk, dtype=torch.int64, device=dev)
             return self._local_search(queries, topk, normalize)
-        sizes = dist_utils.get_varsize(queries)                                    # src/index.py:129
+        sizes = [int(queries.shape[0])] * w if self.equal_batch else dist_utils.get_varsize(queries)   # src/index.py:129
         allqueries = dist_utils.varsize_all_gather(queries, sizes)                 # src/index.py:128
         offs = np.cumsum([0] + sizes)
         if allqueries.shape[0] == 0:

@@ -190,46 +190,52 @@ __device__ __forceinline__ void warp_sort_desc_u64(uint64_t (&key)[E], int lane)
   }
 }
 
-// Block-wide MSB-first bisection over the non-zero 32-bit values v[] (kSelKPT per thread).
-// Invariant: at least kk values are >= prefix.  `prefix` enters with the bits common to every
-// candidate, `top_bit` is the first undecided bit, `n_ge` the number of values >= prefix.  Stops
-// as soon as no more than `stop_at` values remain >= prefix (they then fit the final sort), or
-// when all bits are decided (prefix is then exactly the kk-th largest value).
-__device__ __forceinline__ uint32_t block_bisect(const uint32_t (&v)[kSelKPT], int kk, uint32_t prefix, int top_bit,
-                                                 int& n_ge, int stop_at, int* s_cnt /*[32]*/) {
+// Block-wide MSB-first bisection over the non-zero 32-bit values v[NV] (NV per thread).
+// Invariant: at least kk values are >= prefix.  `prefix` enters with the bits already known,
+// `bit` is the first undecided bit (left at the next undecided bit, -1 when none remain), `n_ge`
+// the number of values >= prefix.  Stops as soon as no more than `stop_at` values remain >= prefix,
+// or when all bits are decided (prefix is then exactly the kk-th largest value).
+template <int NV>
+__device__ __forceinline__ uint32_t block_bisect(const uint32_t (&v)[NV], int kk, uint32_t prefix, int& bit, int& n_ge,
+                                                 int stop_at, int* s_cnt /*[32]*/) {
   if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
   __syncthreads();
 #pragma unroll 1
-  for (int b = top_bit; b >= 0 && n_ge > stop_at; --b) {
-    const uint32_t cand = prefix | (1u << b);
+  while (bit >= 0 && n_ge > stop_at) {
+    const uint32_t cand = prefix | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int j = 0; j < kSelKPT; ++j) c += v[j] >= cand ? 1 : 0;
+    for (int j = 0; j < NV; ++j) c += v[j] >= cand ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt[b], c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt[bit], c);
     __syncthreads();
-    const int tot = s_cnt[b];
+    const int tot = s_cnt[bit];
     if (tot >= kk) { prefix = cand; n_ge = tot; }
+    --bit;
   }
   __syncthreads();
   return prefix;
 }
+
+constexpr int kSelStage2 = kSelThreads;  // survivors of phase 1 are re-bisected one per thread
 
 __global__ void __launch_bounds__(kSelThreads, 1)
 select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int k,
                    int64_t id_base, int64_t id_stride, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_ids) {
   __shared__ int s_cnt[32];
-  __shared__ int s_misc[4];       // [0] #greater, [1] #tied, [2] winner slots, [3] total candidates
+  __shared__ int s_misc[6];       // [0] #greater, [2] winner slots, [3] total candidates, [4] stage-2 slots
   __shared__ uint32_t s_bits[2];  // AND / OR of all candidate score words
   __shared__ uint64_t s_win[kMaxK];
+  __shared__ uint64_t s_key[kSelStage2];
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x < kMaxK) s_win[threadIdx.x] = 0;
-  if (threadIdx.x < 4) s_misc[threadIdx.x] = 0;
+  if (threadIdx.x < 6) s_misc[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_bits[0] = 0xFFFFFFFFu; s_bits[1] = 0u; }
+  s_key[threadIdx.x] = 0;
   __syncthreads();
 
   // warp w owns lists w, w+32, ...; lane owns positions lane, lane+32, ... of each (coalesced)
@@ -266,38 +272,55 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
   }
   __syncthreads();
   const int total = s_misc[3];
-  // 1) raise a score-word threshold t_hi until at most kMaxK candidates are >= t_hi (or until it
-  //    is the exact k-th largest score word when many candidates tie)
+
+  // ---- phase 1 (all candidates, 40 score words per thread): raise the threshold until at most
+  //      kSelStage2 candidates remain above it ----
   uint32_t t_hi = 0;
   int n_ge = total;
-  if (total > kMaxK) {  // block-uniform (k <= kMaxK <= total)
+  int bit = -1;
+  if (total > kMaxK) {  // block-uniform
     const uint32_t diff = s_bits[0] ^ s_bits[1];
     if (diff == 0u) {
-      t_hi = s_bits[1];  // every candidate has the same score
+      t_hi = s_bits[1];  // every candidate has the same score word
     } else {
-      const int top_bit = 31 - __clz(diff);
-      const uint32_t common = top_bit == 31 ? 0u : (s_bits[1] & ~((2u << top_bit) - 1u));
-      t_hi = block_bisect(v, k, common, top_bit, n_ge, kMaxK, s_cnt);
+      bit = 31 - __clz(diff);
+      const uint32_t common = bit == 31 ? 0u : (s_bits[1] & ~((2u << bit) - 1u));
+      t_hi = block_bisect<kSelKPT>(v, k, common, bit, n_ge, kSelStage2, s_cnt);
     }
   }
-  if (n_ge <= kMaxK) {
-    // 2a) common case: the <= kMaxK survivors go to the final sort, which orders full 64-bit keys
-    //     (score, then row) and therefore also resolves ties exactly
+  if (n_ge <= kSelStage2) {
+    // ---- phase 2 (<= 1024 survivors, one per thread): full keys to shared memory, keep bisecting
+    //      until they fit the final sort ----
 #pragma unroll
     for (int i = 0; i < kSelListsPerWarp; ++i) {
 #pragma unroll
       for (int ch = 0; ch < kSelChunks; ++ch) {
         const uint32_t hv = v[i * kSelChunks + ch];
-        if (hv != 0u && hv >= t_hi) {
-          const int slot = atomicAdd(&s_misc[2], 1);
-          if (slot < kMaxK) s_win[slot] = lptr[i][lane + 32 * ch];
-        }
+        if (hv != 0u && hv >= t_hi) s_key[atomicAdd(&s_misc[4], 1)] = lptr[i][lane + 32 * ch];
       }
     }
+    __syncthreads();
+    const uint64_t my_key = s_key[threadIdx.x];   // 0 beyond the survivors
+    uint32_t w1[1] = {static_cast<uint32_t>(my_key >> 32)};
+    if (n_ge > kMaxK) t_hi = block_bisect<1>(w1, k, t_hi, bit, n_ge, kMaxK, s_cnt);
+    if (n_ge <= kMaxK) {
+      // the <= kMaxK survivors go to the final sort, which orders full 64-bit keys (score, then row)
+      // and therefore resolves ties exactly
+      if (my_key != 0ull && w1[0] >= t_hi) s_win[atomicAdd(&s_misc[2], 1)] = my_key;
+    } else {
+      // > kMaxK candidates share the exact k-th largest score word: everything above wins, and a
+      // bisection over the row words of the tied candidates keeps the `need` smallest rows
+      const bool gtr = w1[0] > t_hi;
+      const int gt = __syncthreads_count(gtr);
+      if (gtr) s_win[atomicAdd(&s_misc[2], 1)] = my_key;
+      uint32_t lo1[1] = {(my_key != 0ull && w1[0] == t_hi) ? static_cast<uint32_t>(my_key) : 0u};
+      int n_tie = n_ge - gt, b2 = 31;
+      const uint32_t t_lo = block_bisect<1>(lo1, k - gt, 0u, b2, n_tie, 0, s_cnt);
+      if (lo1[0] != 0u && lo1[0] >= t_lo) s_win[atomicAdd(&s_misc[2], 1)] = my_key;
+    }
   } else {
-    // 2b) more than kMaxK candidates share the boundary score word t_hi (exact k-th largest):
-    //     everything above it wins, and a second bisection over the row words of the tied
-    //     candidates keeps the `need` smallest rows
+    // ---- more than kSelStage2 candidates share the exact k-th largest score word t_hi (massive
+    //      duplicates): same tie rule, in the 40-words-per-thread domain ----
     int gt = 0;
 #pragma unroll
     for (int j = 0; j < kSelKPT; ++j) gt += v[j] > t_hi ? 1 : 0;
@@ -318,8 +341,8 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
     }
     __syncthreads();
     const int need = k - s_misc[0];  // >= 1
-    int n_tie = n_ge - s_misc[0];
-    const uint32_t t_lo = block_bisect(v, need, 0u, 31, n_tie, 0, s_cnt);  // exact need-th largest row word
+    int n_tie = n_ge - s_misc[0], b2 = 31;
+    const uint32_t t_lo = block_bisect<kSelKPT>(v, need, 0u, b2, n_tie, 0, s_cnt);  // exact need-th largest row word
 #pragma unroll
     for (int j = 0; j < kSelKPT; ++j) {
       if (v[j] != 0u && v[j] >= t_lo) {
@@ -329,20 +352,26 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
     }
   }
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  uint64_t w[kMaxK / 32];
-#pragma unroll
-  for (int e = 0; e < kMaxK / 32; ++e) w[e] = s_win[lane * (kMaxK / 32) + e];
-  warp_sort_desc_u64<kMaxK / 32>(w, lane);
-#pragma unroll
-  for (int e = 0; e < kMaxK / 32; ++e) {
-    const int pos = lane * (kMaxK / 32) + e;
-    if (pos < k) {
-      const bool ok = w[e] != 0;
-      const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(w[e]);
-      out_scores[static_cast<int64_t>(q) * k + pos] = ok ? ord_to_f32(static_cast<uint32_t>(w[e] >> 32)) : -INFINITY;
-      out_ids[static_cast<int64_t>(q) * k + pos] = ok ? id_base + static_cast<int64_t>(r) * id_stride : -1;
-    }
+  // ---- final order: rank by counting (128 threads x 128 broadcast reads beat a one-warp sorting
+  //      network by ~10x here); keys are unique, empty slots are 0 ----
+  if (threadIdx.x >= kMaxK) return;
+  const uint64_t mykey = s_win[threadIdx.x];
+  int rank = 0, nvalid = 0;
+#pragma unroll 8
+  for (int j = 0; j < kMaxK; ++j) {
+    const uint64_t o = s_win[j];
+    rank += o > mykey ? 1 : 0;
+    nvalid += o != 0ull ? 1 : 0;
+  }
+  if (mykey != 0ull && rank < k) {
+    const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(mykey);
+    out_scores[static_cast<int64_t>(q) * k + rank] = ord_to_f32(static_cast<uint32_t>(mykey >> 32));
+    out_ids[static_cast<int64_t>(q) * k + rank] = id_base + static_cast<int64_t>(r) * id_stride;
+  }
+  const int p = threadIdx.x;  // padding for queries with fewer than k candidates
+  if (p >= nvalid && p < k) {
+    out_scores[static_cast<int64_t>(q) * k + p] = -INFINITY;
+    out_ids[static_cast<int64_t>(q) * k + p] = -1;
   }
 }
 

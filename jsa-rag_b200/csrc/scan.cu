@@ -297,13 +297,23 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     {
       const uint32_t* qrow = reinterpret_cast<const uint32_t*>(
           static_cast<const uint16_t*>(p.qbuf) + static_cast<size_t>(p.q_row0 + ql) * p.dim);
+      // software-pipelined: the global loads of chunk kc+1 are in flight while chunk kc is stored
+      uint4 nxt[8];
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(qrow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nxt[i] = nk_ts > 0 ? src[i] : make_uint4(0, 0, 0, 0);
+      }
       for (int kc = 0; kc < nk_ts; ++kc) {
         uint32_t w[32];
-        const uint4* src = reinterpret_cast<const uint4*>(qrow + kc * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint4 v = src[i];
-          w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+          w[4 * i + 0] = nxt[i].x; w[4 * i + 1] = nxt[i].y; w[4 * i + 2] = nxt[i].z; w[4 * i + 3] = nxt[i].w;
+        }
+        if (kc + 1 < nk_ts) {
+          const uint4* src = reinterpret_cast<const uint4*>(qrow + (kc + 1) * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) nxt[i] = src[i];
         }
         ptx::tmem_st_32x32b_x32(t_lane + kc * 32, w);
       }
@@ -353,7 +363,23 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
         pm0 &= static_cast<uint32_t>(vm);
         pm1 &= static_cast<uint32_t>(vm >> 32);
       }
-      // ---- rare path: append the survivors (exact key test decides score ties by row) ----
+      // ---- append the survivors (exact key test decides score ties by row) ----
+      if ((pm0 & pm1) == 0xFFFFFFFFu) {
+        // every passage of the tile passes (unseeded first tiles): statically indexed, no select tree
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const uint64_t kk = make_key(__uint_as_float(r0[c]), static_cast<uint32_t>(row0) + c);
+          if (kk > thrkey) my_list[cnt++] = kk;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const uint64_t kk = make_key(__uint_as_float(r1[c]), static_cast<uint32_t>(row0) + 32 + c);
+          if (kk > thrkey) my_list[cnt++] = kk;
+        }
+        st_n += 64;
+        pm0 = pm1 = 0u;
+      }
+      // rare path: a few survivors per tile
       while ((pm0 | pm1) != 0u) {
         int c;
         if (pm0 != 0u) { c = __ffs(pm0) - 1; pm0 &= pm0 - 1u; }

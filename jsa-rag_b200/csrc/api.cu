@@ -122,9 +122,10 @@ WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
   WsLayout w;
   const size_t bpad = align_up(static_cast<size_t>(max_batch > 0 ? max_batch : 1), kNQ);
   const size_t grid = static_cast<size_t>(h->num_sms);
+  const size_t cap = max_k <= kSmallK ? kCap : kCapBig;
   size_t off = 0;
   w.q_off = off;    off += align_up(bpad * h->dim * 2, 1024);
-  w.cand_off = off; off += align_up(grid * kNQ * kCap * sizeof(uint64_t), 1024);
+  w.cand_off = off; off += align_up(grid * kNQ * cap * sizeof(uint64_t), 1024);
   w.pk_off = off;   off += align_up(grid * kNQ * sizeof(int), 1024);
   w.seed_s_off = off; off += align_up(static_cast<size_t>(kNQ) * max_k * sizeof(float), 1024);
   w.seed_i_off = off; off += align_up(static_cast<size_t>(kNQ) * max_k * sizeof(int64_t), 1024);
@@ -284,6 +285,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   p.idesc = ptx::make_idesc_f16(kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
   p.dim = h->dim;
   p.qbuf = qbuf;
+  p.cap = k <= kSmallK ? kCap : kCapBig;
+  p.emit = k <= kSmallK ? kEmit : kCapBig;
   p.cand = reinterpret_cast<uint64_t*>(ws + w.cand_off);
   p.part_cnt = reinterpret_cast<int*>(ws + w.pk_off);
   p.id_base = h->id_base;
@@ -300,7 +303,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   int levels[6];
   int n_levels = 0;
   if (tiles_per_cta >= 8 && !(h->dbg_flags & kDbgNoSeed)) {
-    const int64_t denom = static_cast<int64_t>(grid) * 150;   // target ~150 appended candidates per (CTA, query)
+    // target appended candidates per (CTA, query): ~150 for the 512-slot lists, ~1200 for the 2048-slot ones
+    const int64_t denom = static_cast<int64_t>(grid) * (k <= kSmallK ? 150 : 1200);
     int64_t need = tiles_per_cta;
     int tmp[6];
     int nt = 0;
@@ -310,7 +314,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       if (nxt >= need) break;
       tmp[nt++] = static_cast<int>(nxt);
       need = nxt;
-      if (nxt <= kEmit / kTileN) break;   // an unseeded pass this short leaves <= kEmit candidates per list
+      if (nxt <= p.emit / kTileN) break;   // an unseeded pass this short leaves <= emit candidates per list
     }
     for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
   }
@@ -328,7 +332,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       pp.num_tiles = levels[lv] * grid < num_tiles ? levels[lv] * grid : num_tiles;
       pp.stats = nullptr;
       CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, pp, grid, h->smem_bytes, st));
-      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.batch, k, 0, 1, seed_scores, seed_ids, st));
+      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.cap, p.batch, k, 0, 1, seed_scores, seed_ids, st));
       h->last_launches += 2;
       p.seed = seed_scores;
     }
@@ -336,7 +340,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev0[h->n_timed], st));
     CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, grid, h->smem_bytes, st));
     if (timed) { CUDA_TRY(h, cudaEventRecord(h->ev1[h->n_timed], st)); h->n_timed++; }
-    CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.batch, k, h->id_base, h->id_stride,
+    CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.cap, p.batch, k, h->id_base, h->id_stride,
                               out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
     h->last_launches += 2;
   }

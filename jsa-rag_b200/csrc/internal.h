@@ -18,10 +18,14 @@ constexpr int kMaxStages = 12;
 constexpr int kTmemCols = 512;   // whole TMEM: queries (A operand) + two accumulator buffers
 constexpr int kAccCol0 = kTmemCols - 2 * kTileN;                  // accumulators live in the last 128 columns
 constexpr int kMaxTsChunks = kAccCol0 / (kKChunk / 2);            // 12 K chunks (768 dims) of the queries fit in TMEM
-constexpr int kCap = 512;        // candidate slots per (CTA, query) in the L2-resident candidate lists
-constexpr int kSortE = kCap / 32;  // keys per lane when a warp compacts one list
-constexpr int kEmit = 256;       // a CTA hands at most this many candidates per query to the select kernel
-constexpr int kMaxK = 128;       // largest fused top-k
+// Two list geometries: k <= kSmallK keeps 512-slot lists (register-resident compaction / select),
+// k <= kMaxK uses 2048-slot lists and the streaming variants.
+constexpr int kCap = 512;        // candidate slots per (CTA, query), small-k mode
+constexpr int kSortE = kCap / 32;  // keys per lane when a warp compacts one small list
+constexpr int kEmit = 256;       // small-k mode: a CTA hands at most this many candidates per query to the select kernel
+constexpr int kSmallK = 128;     // largest k of the small (fast) mode
+constexpr int kCapBig = 2048;    // candidate slots per (CTA, query), big-k mode
+constexpr int kMaxK = 1024;      // largest supported top-k
 constexpr int kMaxDim = 1024;
 constexpr int kScanThreads = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue/select
 constexpr int kCtrlBytes = 1024;   // barriers + TMEM base pointer
@@ -40,7 +44,9 @@ struct ScanParams {
   int dim;               // embedding dimension
   const void* qbuf;      // prepared queries [batch_pad, dim] in the index dtype (row-major, zero padded)
   uint32_t idesc;        // tcgen05 instruction descriptor (dtype dependent)
-  uint64_t* cand;        // [grid][kNQ][kCap] packed (orderable score << 32 | ~row) keys
+  int cap;               // slots per candidate list (kCap or kCapBig)
+  int emit;              // lists longer than this are cut back to their best k before they are handed over
+  uint64_t* cand;        // [grid][kNQ][cap] packed (orderable score << 32 | ~row) keys
   int* part_cnt;         // [grid][kNQ] number of candidates each CTA leaves at the head of its lists
   int64_t id_base, id_stride;
   const float* seed;     // optional [kNQ][k] sorted scores of the sampled pre-pass (NULL = none)
@@ -64,8 +70,9 @@ cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, co
 cudaError_t configure_scan(size_t smem_bytes);
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
                          int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st);
-cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int batch, int k, int64_t id_base,
-                          int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st);
+cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int cap, int batch, int k,
+                          int64_t id_base, int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st);
+cudaError_t configure_merge();
 cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, const int64_t* rows, int64_t n,
                                void* out, cudaStream_t st);
 

@@ -15,8 +15,6 @@
 
 namespace mips {
 
-constexpr int kMergeE = kMaxK / 32;   // 4 entries per lane -> KP = 128
-constexpr int kMergeKP = 32 * kMergeE;
 constexpr int kMergeWarps = 8;
 constexpr int64_t kPadId = INT64_MAX;
 
@@ -36,8 +34,10 @@ __device__ __forceinline__ Cand shfl_xor_cand(const Cand& c, int lmask) {
   return o;
 }
 
-// v holds a bitonic sequence of KP entries (position i = lane*E + e); sorts it descending.
+// v holds a bitonic sequence of KP = 32*E entries (position i = lane*E + e); sorts it descending.
+template <int kMergeE>
 __device__ __forceinline__ void bitonic_merge_desc(Cand (&v)[kMergeE], int lane) {
+  constexpr int kMergeKP = 32 * kMergeE;
 #pragma unroll
   for (int j = kMergeKP >> 1; j >= 1; j >>= 1) {
     if (j < kMergeE) {
@@ -78,12 +78,15 @@ __device__ __forceinline__ Cand load_cand(const float* s, const int64_t* ids, in
   return c;
 }
 
+template <int kMergeE>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int num_lists,
                   int64_t list_stride, int k_in, int k_out, float* __restrict__ out_scores,
                   int64_t* __restrict__ out_ids) {
-  __shared__ uint32_t sh_ord[kMergeWarps][kMergeKP];
-  __shared__ int64_t sh_id[kMergeWarps][kMergeKP];
+  constexpr int kMergeKP = 32 * kMergeE;
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  int64_t (*sh_id)[kMergeKP] = reinterpret_cast<int64_t (*)[kMergeKP]>(merge_smem);
+  uint32_t (*sh_ord)[kMergeKP] = reinterpret_cast<uint32_t (*)[kMergeKP]>(merge_smem + sizeof(int64_t) * kMergeWarps * kMergeKP);
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,7 +109,7 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
         const Cand b = load_cand(s, id, kMergeKP - 1 - (lane * kMergeE + e), k_in);
         if (better(b, acc[e])) acc[e] = b;
       }
-      bitonic_merge_desc(acc, lane);
+      bitonic_merge_desc<kMergeE>(acc, lane);
     }
   }
 #pragma unroll
@@ -125,7 +128,7 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
       b.id = sh_id[w][pos];
       if (better(b, acc[e])) acc[e] = b;
     }
-    bitonic_merge_desc(acc, lane);
+    bitonic_merge_desc<kMergeE>(acc, lane);
   }
 #pragma unroll
   for (int e = 0; e < kMergeE; ++e) {
@@ -226,13 +229,13 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
   __shared__ int s_cnt[32];
   __shared__ int s_misc[6];       // [0] #greater, [2] winner slots, [3] total candidates, [4] stage-2 slots
   __shared__ uint32_t s_bits[2];  // AND / OR of all candidate score words
-  __shared__ uint64_t s_win[kMaxK];
+  __shared__ uint64_t s_win[kSmallK];
   __shared__ uint64_t s_key[kSelStage2];
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (threadIdx.x < kMaxK) s_win[threadIdx.x] = 0;
+  if (threadIdx.x < kSmallK) s_win[threadIdx.x] = 0;
   if (threadIdx.x < 6) s_misc[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_bits[0] = 0xFFFFFFFFu; s_bits[1] = 0u; }
   s_key[threadIdx.x] = 0;
@@ -278,7 +281,7 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
   uint32_t t_hi = 0;
   int n_ge = total;
   int bit = -1;
-  if (total > kMaxK) {  // block-uniform
+  if (total > kSmallK) {  // block-uniform
     const uint32_t diff = s_bits[0] ^ s_bits[1];
     if (diff == 0u) {
       t_hi = s_bits[1];  // every candidate has the same score word
@@ -302,13 +305,13 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
     __syncthreads();
     const uint64_t my_key = s_key[threadIdx.x];   // 0 beyond the survivors
     uint32_t w1[1] = {static_cast<uint32_t>(my_key >> 32)};
-    if (n_ge > kMaxK) t_hi = block_bisect<1>(w1, k, t_hi, bit, n_ge, kMaxK, s_cnt);
-    if (n_ge <= kMaxK) {
-      // the <= kMaxK survivors go to the final sort, which orders full 64-bit keys (score, then row)
+    if (n_ge > kSmallK) t_hi = block_bisect<1>(w1, k, t_hi, bit, n_ge, kSmallK, s_cnt);
+    if (n_ge <= kSmallK) {
+      // the <= kSmallK survivors go to the final sort, which orders full 64-bit keys (score, then row)
       // and therefore resolves ties exactly
       if (my_key != 0ull && w1[0] >= t_hi) s_win[atomicAdd(&s_misc[2], 1)] = my_key;
     } else {
-      // > kMaxK candidates share the exact k-th largest score word: everything above wins, and a
+      // > kSmallK candidates share the exact k-th largest score word: everything above wins, and a
       // bisection over the row words of the tied candidates keeps the `need` smallest rows
       const bool gtr = w1[0] > t_hi;
       const int gt = __syncthreads_count(gtr);
@@ -333,7 +336,7 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
         const int j = i * kSelChunks + ch;
         if (v[j] > t_hi) {
           const int slot = atomicAdd(&s_misc[2], 1);
-          if (slot < kMaxK) s_win[slot] = lptr[i][lane + 32 * ch];
+          if (slot < kSmallK) s_win[slot] = lptr[i][lane + 32 * ch];
         }
         const bool tie = v[j] == t_hi && v[j] != 0u;
         v[j] = tie ? static_cast<uint32_t>(lptr[i][lane + 32 * ch]) : 0u;
@@ -347,18 +350,18 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
     for (int j = 0; j < kSelKPT; ++j) {
       if (v[j] != 0u && v[j] >= t_lo) {
         const int slot = atomicAdd(&s_misc[2], 1);
-        if (slot < kMaxK) s_win[slot] = (static_cast<uint64_t>(t_hi) << 32) | v[j];
+        if (slot < kSmallK) s_win[slot] = (static_cast<uint64_t>(t_hi) << 32) | v[j];
       }
     }
   }
   __syncthreads();
   // ---- final order: rank by counting (128 threads x 128 broadcast reads beat a one-warp sorting
   //      network by ~10x here); keys are unique, empty slots are 0 ----
-  if (threadIdx.x >= kMaxK) return;
+  if (threadIdx.x >= kSmallK) return;
   const uint64_t mykey = s_win[threadIdx.x];
   int rank = 0, nvalid = 0;
 #pragma unroll 8
-  for (int j = 0; j < kMaxK; ++j) {
+  for (int j = 0; j < kSmallK; ++j) {
     const uint64_t o = s_win[j];
     rank += o > mykey ? 1 : 0;
     nvalid += o != 0ull ? 1 : 0;
@@ -375,21 +378,158 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
   }
 }
 
-cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int batch, int k, int64_t id_base,
-                          int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------------
+// Big-k select (128 < k <= 1024, lists of up to kCapBig entries): same bisection, but the score
+// words are re-read from the L2-resident lists on every step instead of living in registers; once
+// at most kBigStage (2048) candidates remain they are ranked by counting in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBigStage = 2048;
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int cap,
+                       int k, int64_t id_base, int64_t id_stride, float* __restrict__ out_scores,
+                       int64_t* __restrict__ out_ids) {
+  __shared__ int s_misc[4];       // [0] scratch count, [2] survivor slots
+  __shared__ uint32_t s_bits[2];
+  __shared__ int s_len[kSelMaxLists];
+  __shared__ uint64_t s_key[kBigStage];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kBigStage; i += kSelThreads) s_key[i] = 0;
+  if (threadIdx.x < 4) s_misc[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_bits[0] = 0xFFFFFFFFu; s_bits[1] = 0u; }
+  if (threadIdx.x < kSelMaxLists) {
+    int c = threadIdx.x < num_lists ? part_cnt[threadIdx.x * kNQ + q] : 0;
+    s_len[threadIdx.x] = c > cap ? cap : c;
+  }
+  __syncthreads();
+
+  // one pass over every candidate of this query: warp w takes lists w, w+32, ...; f(hi, lo) per entry
+  auto for_each = [&](auto&& f) {
+    for (int l = warp; l < num_lists; l += kSelWarps) {
+      const uint64_t* lst = cand + (static_cast<size_t>(l) * kNQ + q) * cap;
+      const int c = s_len[l];
+      for (int i = lane; i < c; i += 32) f(lst[i]);
+    }
+  };
+  auto block_sum = [&](int v) -> int {   // all threads must call
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if (threadIdx.x == 0) s_misc[0] = 0;
+    __syncthreads();
+    if (lane == 0 && v) atomicAdd(&s_misc[0], v);
+    __syncthreads();
+    return s_misc[0];
+  };
+
+  uint32_t and_v = 0xFFFFFFFFu, or_v = 0u;
+  int mine = 0;
+  for_each([&](uint64_t kk) { const uint32_t h = static_cast<uint32_t>(kk >> 32); and_v &= h; or_v |= h; ++mine; });
+  and_v = __reduce_and_sync(0xffffffffu, and_v);
+  or_v = __reduce_or_sync(0xffffffffu, or_v);
+  if (lane == 0) { atomicAnd(&s_bits[0], and_v); atomicOr(&s_bits[1], or_v); }
+  const int total = block_sum(mine);
+
+  uint32_t t_hi = 0;
+  int n_ge = total;
+  if (total > kBigStage) {
+    const uint32_t diff = s_bits[0] ^ s_bits[1];
+    int bit = diff == 0u ? -1 : 31 - __clz(diff);
+    t_hi = (diff == 0u || bit == 31) ? (diff == 0u ? s_bits[1] : 0u) : (s_bits[1] & ~((2u << bit) - 1u));
+    while (bit >= 0 && n_ge > kBigStage) {
+      const uint32_t c0 = t_hi | (1u << bit);
+      int n = 0;
+      for_each([&](uint64_t kk) { n += static_cast<uint32_t>(kk >> 32) >= c0 ? 1 : 0; });
+      const int tot = block_sum(n);
+      if (tot >= k) { t_hi = c0; n_ge = tot; }
+      --bit;
+    }
+  }
+  uint64_t thrkey = static_cast<uint64_t>(t_hi) << 32;
+  if (n_ge > kBigStage) {
+    // more than kBigStage candidates share the exact k-th largest score word: bisect the row words of the ties
+    int n = 0;
+    for_each([&](uint64_t kk) { n += static_cast<uint32_t>(kk >> 32) > t_hi ? 1 : 0; });
+    const int need = k - block_sum(n);
+    uint32_t t_lo = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t c0 = t_lo | (1u << bit);
+      int m2 = 0;
+      for_each([&](uint64_t kk) {
+        m2 += (static_cast<uint32_t>(kk >> 32) == t_hi && static_cast<uint32_t>(kk) >= c0) ? 1 : 0;
+      });
+      if (block_sum(m2) >= need) t_lo = c0;
+    }
+    thrkey |= t_lo;   // now exactly k candidates have key >= thrkey
+  }
+  for_each([&](uint64_t kk) {
+    if (kk >= thrkey) {
+      const int slot = atomicAdd(&s_misc[2], 1);
+      if (slot < kBigStage) s_key[slot] = kk;
+    }
+  });
+  __syncthreads();
+  // rank by counting: 2 keys per thread against all survivors (broadcast reads); keys are unique
+  const int nsurv = s_misc[2] < kBigStage ? s_misc[2] : kBigStage;
+  const uint64_t k0 = s_key[threadIdx.x], k1 = s_key[threadIdx.x + kSelThreads];
+  int r0 = 0, r1 = 0;
+  for (int j = 0; j < nsurv; ++j) {
+    const uint64_t o = s_key[j];
+    r0 += o > k0 ? 1 : 0;
+    r1 += o > k1 ? 1 : 0;
+  }
+  auto emit = [&](uint64_t kk, int rank) {
+    if (kk != 0ull && rank < k) {
+      const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(kk);
+      out_scores[static_cast<int64_t>(q) * k + rank] = ord_to_f32(static_cast<uint32_t>(kk >> 32));
+      out_ids[static_cast<int64_t>(q) * k + rank] = id_base + static_cast<int64_t>(r) * id_stride;
+    }
+  };
+  emit(k0, r0);
+  emit(k1, r1);
+  for (int p = nsurv + threadIdx.x; p < k; p += kSelThreads) {   // fewer than k candidates: pad
+    out_scores[static_cast<int64_t>(q) * k + p] = -INFINITY;
+    out_ids[static_cast<int64_t>(q) * k + p] = -1;
+  }
+}
+
+cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int cap, int batch, int k,
+                          int64_t id_base, int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (batch == 0) return cudaSuccess;
   if (num_lists > kSelMaxLists) return cudaErrorInvalidValue;
-  select_topk_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, k, id_base, id_stride, out_scores,
-                                                    out_ids);
+  if (cap == kCap && k <= kSmallK)
+    select_topk_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, k, id_base, id_stride, out_scores,
+                                                      out_ids);
+  else
+    select_topk_big_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, cap, k, id_base, id_stride,
+                                                          out_scores, out_ids);
   return cudaGetLastError();
+}
+
+template <int E>
+static cudaError_t launch_merge_e(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
+                                  int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(kMergeWarps) * 32 * E * (sizeof(int64_t) + sizeof(uint32_t));
+  merge_topk_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(scores, ids, num_lists, list_stride, k_in, k_out,
+                                                             out_scores, out_ids);
+  return cudaGetLastError();
+}
+
+cudaError_t configure_merge() {
+  return cudaFuncSetAttribute(merge_topk_kernel<kMaxK / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kMergeWarps * kMaxK * static_cast<int>(sizeof(int64_t) + sizeof(uint32_t)));
 }
 
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
                          int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (batch == 0) return cudaSuccess;
-  merge_topk_kernel<<<batch, kMergeWarps * 32, 0, st>>>(scores, ids, num_lists, list_stride, k_in, k_out, out_scores,
-                                                       out_ids);
-  return cudaGetLastError();
+  const int kk = k_in > k_out ? k_in : k_out;
+  if (kk <= kSmallK)
+    return launch_merge_e<kSmallK / 32>(scores, ids, num_lists, list_stride, batch, k_in, k_out, out_scores, out_ids, st);
+  static cudaError_t cfg = configure_merge();
+  if (cfg != cudaSuccess) return cfg;
+  return launch_merge_e<kMaxK / 32>(scores, ids, num_lists, list_stride, batch, k_in, k_out, out_scores, out_ids, st);
 }
 
 }  // namespace mips

@@ -112,6 +112,62 @@ __device__ __noinline__ uint64_t compact_list(uint64_t* __restrict__ list, int c
   return thrkey;
 }
 
+// Same contract for lists of any length (big-k mode): nothing is kept in registers, every bisection
+// step re-reads the (L2-resident) list.  Slow (~32 passes) but only reached when a list overflows,
+// which seeded thresholds make a rare event.  Whole warp, converged; requires c > k.
+__device__ __noinline__ uint64_t compact_list_stream(uint64_t* __restrict__ list, int c, int k, int lane) {
+  const uint32_t* hi_words = reinterpret_cast<const uint32_t*>(list) + 1;   // little endian: high word second
+  const uint32_t* lo_words = reinterpret_cast<const uint32_t*>(list);
+  uint32_t t_hi = 0;
+#pragma unroll 1
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t cand = t_hi | (1u << b);
+    int n = 0;
+    for (int i = lane; i < c; i += 32) n += hi_words[2 * i] >= cand ? 1 : 0;
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (n >= k) t_hi = cand;
+  }
+  int gt = 0, eq = 0;
+  for (int i = lane; i < c; i += 32) {
+    const uint32_t h = hi_words[2 * i];
+    gt += h > t_hi ? 1 : 0;
+    eq += h == t_hi ? 1 : 0;
+  }
+  gt = __reduce_add_sync(0xffffffffu, gt);
+  eq = __reduce_add_sync(0xffffffffu, eq);
+  const int need = k - gt;
+  uint32_t t_lo = 0;   // need == eq: every tied entry is kept
+  if (need < eq) {
+#pragma unroll 1
+    for (int b = 31; b >= 0; --b) {
+      const uint32_t cand = t_lo | (1u << b);
+      int n = 0;
+      for (int i = lane; i < c; i += 32) n += (hi_words[2 * i] == t_hi && lo_words[2 * i] >= cand) ? 1 : 0;
+      n = __reduce_add_sync(0xffffffffu, n);
+      if (n >= need) t_lo = cand;
+    }
+  } else {
+    uint32_t m = 0xFFFFFFFFu;
+    for (int i = lane; i < c; i += 32)
+      if (hi_words[2 * i] == t_hi) m = min(m, lo_words[2 * i]);
+    t_lo = __reduce_min_sync(0xffffffffu, m);
+  }
+  const uint64_t thrkey = (static_cast<uint64_t>(t_hi) << 32) | t_lo;
+  // in-place stream compaction, 32 entries at a time (writes never pass the reads)
+  int out = 0;
+  for (int base = 0; base < c; base += 32) {
+    const int i = base + lane;
+    const uint64_t kk = i < c ? list[i] : 0ull;
+    const bool keep = kk >= thrkey && i < c;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) list[out + __popc(m & ((1u << lane) - 1u))] = kk;
+    out += __popc(m);
+  }
+  __syncwarp();
+  return thrkey;
+}
+
 // r[c] for a runtime c in [0, 64): registers cannot be indexed dynamically, so pick through a
 // 6-level select tree (63 selects; only executed for the rare survivors).
 __device__ __forceinline__ uint32_t pick64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int c) {
@@ -289,8 +345,9 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     const int ql = quarter * per_warp + (lane_ok ? lane : 0);   // my query within the pass
     const bool live = lane_ok && ql < p.batch;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint64_t* warp_lists = p.cand + (static_cast<size_t>(blockIdx.x) * kNQ + quarter * per_warp) * kCap;
-    uint64_t* my_list = warp_lists + static_cast<size_t>(lane_ok ? lane : 0) * kCap;
+    const int cap = p.cap;
+    uint64_t* warp_lists = p.cand + (static_cast<size_t>(blockIdx.x) * kNQ + quarter * per_warp) * cap;
+    uint64_t* my_list = warp_lists + static_cast<size_t>(lane_ok ? lane : 0) * cap;
     const bool no_select = (p.flags & kDbgNoSelect) != 0;
 
     // ---- queries -> TMEM (A operand, K-major: column c of a chunk holds elements 2c, 2c+1) ----
@@ -394,12 +451,13 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       __syncwarp();
       if (want_stats) { const long long w1 = clock64(); st_b += w1 - w0; w0 = w1; }
       // ---- lists that could overflow during the next tile are cut back to their best k ----
-      uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - kTileN);
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > cap - kTileN);
       while (need != 0u) {  // warp-uniform
         const int l = __ffs(need) - 1;
         need &= need - 1u;
         const int c = __shfl_sync(0xffffffffu, cnt, l);
-        const uint64_t nk_key = compact_list(warp_lists + static_cast<size_t>(l) * kCap, c, p.k, lane);
+        uint64_t* lst = warp_lists + static_cast<size_t>(l) * cap;
+        const uint64_t nk_key = cap == kCap ? compact_list(lst, c, p.k, lane) : compact_list_stream(lst, c, p.k, lane);
         if (lane == l) {
           thrkey = nk_key;
           thr = ord_to_f32(static_cast<uint32_t>(nk_key >> 32));
@@ -412,14 +470,15 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
 
     // ---------------- final: publish this CTA's candidate counts ----------------
     // The candidate lists stay where they are (L2-resident workspace); the select kernel reads
-    // them directly.  Only lists longer than kEmit are first cut down to their best k.
+    // them directly.  Only lists longer than p.emit are first cut down to their best k.
     if (!no_select) {
-      uint32_t need = __ballot_sync(0xffffffffu, cnt > kEmit);
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > p.emit);
       while (need != 0u) {
         const int l = __ffs(need) - 1;
         need &= need - 1u;
         const int c = __shfl_sync(0xffffffffu, cnt, l);
-        compact_list(warp_lists + static_cast<size_t>(l) * kCap, c, p.k, lane);
+        uint64_t* lst = warp_lists + static_cast<size_t>(l) * cap;
+        if (cap == kCap) compact_list(lst, c, p.k, lane); else compact_list_stream(lst, c, p.k, lane);
         if (lane == l) cnt = p.k;
         ++st_m;
       }

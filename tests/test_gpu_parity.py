@@ -130,6 +130,34 @@ def test_matches_fp32_oracle_bitwise_ids(eng, dev, n, d, b, k, dtype):
     assert rep["near_tie_diffs"] <= max(1, b * k // 200)
 
 
+@pytest.mark.parametrize("n,b,k", [(3000, 5, 1000), (200_000, 64, 1000), (50_000, 130, 129), (100_000, 9, 512),
+                                   (1_500_000, 64, 1024), (1024, 3, 1024)])
+def test_large_k(eng, dev, n, b, k):
+    """k in (128, 1024] (BASELINE configs[4] sweeps k = 1000): 2048-slot lists + streaming select."""
+    e, q = _synth(n, 768, b, 77 + k, dev)
+    m = _engine(eng, e)
+    s, i = m.search(q, k)
+    rs, ri = _torch_ref(e, q, k)
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    exact = (q.half().double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]
+    assert rep["near_tie_diffs"] <= max(2, b * k // 200)
+    # ties at large k: duplicated rows, (score desc, id asc) order must be exact
+    if n <= 50_000:
+        e2 = e[: n // 4].repeat(4, 1)
+        m.bind(e2)
+        s2, i2 = m.search(q[:3], k)
+        rs2, ri2 = _torch_ref(e2, q[:3], k)
+        assert torch.equal(i2, ri2)
+    # cross-rank merge at large k
+    W = 4
+    parts = [_engine(eng, e[r::W].contiguous(), id_base=r, id_stride=W).search(q, k) for r in range(W)] if n >= W * k else None
+    if parts:
+        ms, mi = eng.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+        assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
 def test_ties_are_broken_by_ascending_id(eng, dev):
     z = torch.zeros(5000, 768, dtype=torch.float16, device=dev)          # init_embeddings() state: all scores 0
     m = _engine(eng, z)
@@ -184,8 +212,10 @@ def test_error_codes_and_limits(eng, dev):
     m = _engine(eng, e)
     with pytest.raises(RuntimeError, match="selected index k out of range"):
         m.search(q, 501)
+    big, _ = _synth(2000, 768, 1, 2, dev)
+    mb = _engine(eng, big)
     with pytest.raises(ValueError):
-        m.search(q, eng._native.load().mips_max_k() + 1)
+        mb.search(q, eng._native.load().mips_max_k() + 1)
     with pytest.raises(ValueError):
         m.search(q[:, :100], 5)
     with pytest.raises(ValueError):

@@ -15,6 +15,13 @@ def __getattr__(name):  # lazy: engine imports need the CUDA extension
     if name in ("MipsEngine", "merge_topk"):
         from . import engine
         return getattr(engine, name)
+    if name in ("B200ServerIndex", "IndexHolder", "create_app", "RetrieveRequest", "rebuildRequest",
+                "append_embedding_batch", "iter_embedding_stream", "get_pkl_files_in_directory"):
+        from . import server
+        return getattr(server, name)
+    if name == "call_retrieve_api":
+        from . import client
+        return client.call_retrieve_api
     raise AttributeError(name)
 
 

@@ -1,0 +1,203 @@
+"""Index server — same request/response contract as the reference's faiss server
+(build_server/server_start.py), backed by the B200 engine.
+
+    POST /retrieve {"query_embs": [bsz*dim floats], "bsz": int = 1, "topk": int = 10} -> [docs, scores]
+    POST /rebuild  {"checkpoint_path": str, "response_url": str}                     -> swaps the index
+
+Reference semantics kept (build_server/server_start.py:139-163): queries are L2-normalised
+(faiss.normalize_L2; passages are NOT normalised), exact inner product over fp16-stored vectors,
+ids = global insertion order across the embedding files (IndexShards(successive_ids=True), :45),
+file i -> GPU i (:75-77,97).  Differences underneath: the pickle streams are read ONCE straight
+into the device matrix (the reference unpickles everything twice, :63-95), each GPU runs the fused
+scan, the per-GPU top-k are merged on device 0, and /rebuild swaps the index atomically (a search in
+flight keeps the old index alive).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .engine import MipsEngine, merge_topk
+
+try:  # FastAPI is only needed for the HTTP shell, not for the index itself
+    from fastapi import FastAPI, HTTPException
+    from pydantic import BaseModel
+
+    class RetrieveRequest(BaseModel):   # build_server/server_start.py:18-21
+        query_embs: list
+        bsz: int = 1
+        topk: int = 10
+
+    class rebuildRequest(BaseModel):    # build_server/server_start.py:23-25
+        checkpoint_path: str
+        response_url: str
+except ImportError:  # pragma: no cover
+    FastAPI = None
+
+
+def iter_embedding_stream(path: str):
+    """Yields the batches appended by the reference's builder: each ``pickle.dump`` is a list of
+    ``{"emb": np.ndarray[dim], "passage": dict}`` (build_server/index.py:108-111)."""
+    with open(path, "rb") as f:
+        while True:
+            try:
+                yield pickle.load(f)
+            except EOFError:
+                return
+
+
+def append_embedding_batch(path: str, embs: np.ndarray, passages: Sequence[dict]) -> None:
+    """Writes one batch in the reference's stream format (used by tests / tooling)."""
+    with open(path, "ab") as f:
+        pickle.dump([{"emb": embs[i], "passage": passages[i]} for i in range(len(passages))], f)
+
+
+def get_pkl_files_in_directory(directory: str) -> List[str]:
+    """build_server/server_start.py:164-170 (os.walk order is not sorted there; it is here)."""
+    out = []
+    for root, _, files in os.walk(directory):
+        for file in sorted(files):
+            if file.endswith(".pkl"):
+                out.append(os.path.join(root, file))
+    return sorted(out)
+
+
+class B200ServerIndex(object):
+    """Drop-in for ``DistributedFaissIndex`` (build_server/server_start.py:30-163)."""
+
+    def __init__(self, embedding_file_pathes: Sequence[str], checkpoint_pathes=None, gpu_ids: Optional[Sequence[int]] = None,
+                 dtype: torch.dtype = torch.float16, dimension: Optional[int] = None):
+        n_dev = torch.cuda.device_count() if torch.cuda.is_available() else 0
+        if n_dev == 0:
+            raise RuntimeError("B200ServerIndex needs CUDA devices; there is no CPU fallback")
+        gpu_ids = list(range(min(len(embedding_file_pathes), n_dev))) if gpu_ids is None else list(gpu_ids)
+        for g in gpu_ids:
+            if g >= n_dev:
+                raise ValueError(f"GPU {g} not available (Total GPUs: {n_dev})")   # server_start.py:50-51
+        if len(embedding_file_pathes) > len(gpu_ids):
+            raise ValueError("more embedding files than GPUs: the reference maps file i to GPU i")
+        self.doc_map = {}
+        self.shards: List[MipsEngine] = []
+        self.dtype = dtype
+        last_id = 0
+        for file_idx, path in enumerate(embedding_file_pathes):
+            dev = torch.device("cuda", gpu_ids[file_idx])
+            chunks = []
+            first = last_id
+            for batch in iter_embedding_stream(path):                  # one pass (reference: two)
+                embs = np.stack([np.asarray(d["emb"]) for d in batch]).astype(np.float16, copy=False)
+                for d in batch:
+                    self.doc_map[last_id] = d["passage"]                  # server_start.py:84-87
+                    last_id += 1
+                chunks.append(torch.from_numpy(embs))
+            if not chunks:
+                continue
+            dim = int(chunks[0].shape[1]) if dimension is None else int(dimension)
+            n = sum(c.shape[0] for c in chunks)
+            store = torch.empty(n, dim, dtype=dtype, device=dev)
+            at = 0
+            for c in chunks:
+                store[at:at + c.shape[0]].copy_(c, non_blocking=True)
+                at += c.shape[0]
+            eng = MipsEngine(dim, dtype, dev)
+            eng.bind(store, id_base=first, id_stride=1)                   # successive ids across shards
+            self.shards.append(eng)
+        if not self.shards:
+            raise ValueError("no embeddings found")
+        self.dimension = self.shards[0].dim
+        self.ntotal = last_id
+
+    @torch.no_grad()
+    def search(self, query_embs: torch.Tensor, topk: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """normalize_L2(q) -> exact IP top-k on every shard -> merge on the first device."""
+        q = query_embs.to(torch.float32)
+        parts_s, parts_i = [], []
+        for eng in self.shards:
+            with torch.cuda.device(eng.device):
+                s, i = eng.search(q.to(eng.device, non_blocking=True), min(topk, eng.n_local), normalize=True)
+            parts_s.append(s)
+            parts_i.append(i)
+        if len(self.shards) == 1 and parts_s[0].shape[1] == topk:
+            return parts_s[0], parts_i[0]
+        dev0 = self.shards[0].device
+        kmax = max(p.shape[1] for p in parts_s)
+        ss = torch.full((len(parts_s), q.shape[0], kmax), float("-inf"), device=dev0)
+        ii = torch.full((len(parts_s), q.shape[0], kmax), -1, dtype=torch.int64, device=dev0)
+        for n, (s, i) in enumerate(zip(parts_s, parts_i)):
+            torch.cuda.synchronize(s.device)
+            ss[n, :, : s.shape[1]] = s.to(dev0)
+            ii[n, :, : i.shape[1]] = i.to(dev0)
+        with torch.cuda.device(dev0):
+            return merge_topk(ss, ii, topk)
+
+    def search_knn(self, query_embs, topk):
+        """build_server/server_start.py:139-163: returns (all_docs, all_scores) nested lists."""
+        if int(topk) > self.ntotal:
+            raise RuntimeError("selected index k out of range")
+        D, I = self.search(torch.as_tensor(query_embs), int(topk))
+        D, I = D.cpu(), I.cpu()
+        all_docs = [[self.doc_map[int(i)] for i in row] for row in I]
+        all_scores = [[float(x) for x in row] for row in D]
+        return all_docs, all_scores
+
+
+class IndexHolder(object):
+    """Atomically swappable reference to the live index (the reference mutates a module global while
+    `async def retrieve` may be running, server_start.py:181-196)."""
+
+    def __init__(self, index=None):
+        self._index = index
+        self._lock = threading.Lock()
+
+    def get(self):
+        with self._lock:
+            return self._index
+
+    def swap(self, index):
+        with self._lock:
+            old, self._index = self._index, index
+        return old
+
+
+def create_app(holder: IndexHolder, rebuild_fn=None, notify=None):
+    """FastAPI app with the reference's two routes (server_start.py:181-196)."""
+    if FastAPI is None:
+        raise RuntimeError("fastapi / pydantic are required for the HTTP server")
+    app = FastAPI()
+
+    @app.post("/retrieve")
+    async def retrieve(request: RetrieveRequest):
+        index = holder.get()
+        if index is None:
+            raise HTTPException(status_code=500, detail="Index is not ready")      # :184-185
+        query_embs = torch.tensor(request.query_embs).view(request.bsz, -1)          # :186
+        relevant_docs, scores = index.search_knn(query_embs, request.topk)           # :188
+        return [relevant_docs, scores]                                              # :189
+
+    @app.post("/rebuild")
+    def rebuild(request: rebuildRequest):
+        if rebuild_fn is None:
+            raise HTTPException(status_code=501, detail="rebuild is not configured")
+        holder.swap(rebuild_fn(request.checkpoint_path))                             # :193-195
+        if notify is not None:
+            notify(request.response_url, {"status": "success"})                      # :196
+        else:
+            import requests
+            requests.post(request.response_url, json={"status": "success"})
+        return {"status": "success"}
+
+    return app
+
+
+def serve(embedding_dir: str, host: str = "0.0.0.0", port: int = 29501, gpu_ids=None):  # pragma: no cover
+    """`python -m` entry: the reference hard-codes directory and port (server_start.py:171-175,201)."""
+    import uvicorn
+
+    files = get_pkl_files_in_directory(embedding_dir)
+    holder = IndexHolder(B200ServerIndex(files, None, gpu_ids=gpu_ids))
+    uvicorn.run(create_app(holder, rebuild_fn=lambda ckpt: B200ServerIndex(files, ckpt, gpu_ids=gpu_ids)), host=host, port=port)

@@ -302,7 +302,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   const int tiles_per_cta = (num_tiles + grid - 1) / grid;
   int levels[6];
   int n_levels = 0;
-  if (tiles_per_cta >= 8 && !(h->dbg_flags & kDbgNoSeed)) {
+  if (tiles_per_cta > p.emit / kTileN && !(h->dbg_flags & kDbgNoSeed)) {   // longer unseeded scans would overflow `emit`
     // target appended candidates per (CTA, query): ~150 for the 512-slot lists, ~1200 for the 2048-slot ones
     const int64_t denom = static_cast<int64_t>(grid) * (k <= kSmallK ? 150 : 1200);
     int64_t need = tiles_per_cta;

@@ -229,17 +229,27 @@ class B200Index(object):
         ids_np = my_ids.cpu().numpy()
         if w == 1:
             loc = (ids_np - self._id_base) // self._id_stride
-            return [[self.doc_map[int(x)] for x in row] for row in loc]
+            return self._doc_table()[loc].tolist()      # one vectorised gather instead of b*k dict lookups
         all_ids, _ = self._last_all
         all_np = all_ids.cpu().numpy().reshape(-1)
         owner, local = self._owner_and_local(all_np)
-        mine = {}
-        for g, l in zip(all_np[owner == r].tolist(), local[owner == r].tolist()):
-            mine[g] = self.doc_map[l]
+        sel = owner == r
+        mine = dict(zip(all_np[sel].tolist(), self._doc_table()[local[sel]].tolist()))
         merged = {}
         for part in dist_utils.all_gather_object(mine):
             merged.update(part)
         return [[merged[int(g)] for g in row] for row in ids_np]
+
+    def _doc_table(self) -> np.ndarray:
+        """doc_map ({local row -> passage dict}, the reference's public attribute) as an object array,
+        rebuilt only when the dict object or its size changes."""
+        key = (id(self.doc_map), len(self.doc_map))
+        if getattr(self, "_doc_table_key", None) != key:
+            tab = np.empty(len(self.doc_map), dtype=object)
+            for i in range(len(self.doc_map)):
+                tab[i] = self.doc_map[i]
+            self._doc_table_arr, self._doc_table_key = tab, key
+        return self._doc_table_arr
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()

@@ -104,6 +104,12 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
 int mips_merge_topk(int device, const float* scores, const int64_t* ids, int num_lists, int batch,
                     int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream);
 
+/* Same with independent list strides (in elements) for the score and id arrays, so that both can
+ * live in ONE all-gathered buffer per rank ([scores | ids] blocks) and the exchange is a single collective. */
+int mips_merge_topk_strided(int device, const float* scores, const int64_t* ids, int num_lists,
+                            int64_t score_list_stride, int64_t id_list_stride, int batch, int k_in, int k_out,
+                            float* out_scores, int64_t* out_ids, void* stream);
+
 /*
  * out[i, :] = embeddings[local_rows[i], :]   (index dtype, [n, dim] row-major).
  * Replaces: self.embeddings[:, indices.view(-1)] of the 3-tuple search_knn

@@ -29,6 +29,8 @@ SYMBOLS = {
     "mips_search_local": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "mips_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mips_merge_topk_strided": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p]),
     "mips_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "mips_search_host": (c_int, [c_void_p, POINTER(c_float), c_int, c_int, c_int, POINTER(c_float), POINTER(c_int64),
                                  c_void_p]),

@@ -347,18 +347,26 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   return MIPS_OK;
 }
 
-int mips_merge_topk(int device, const float* scores, const int64_t* ids, int num_lists, int batch, int k_in, int k_out,
-                    float* out_scores, int64_t* out_ids, void* stream) {
+int mips_merge_topk_strided(int device, const float* scores, const int64_t* ids, int num_lists,
+                            int64_t score_list_stride, int64_t id_list_stride, int batch, int k_in, int k_out,
+                            float* out_scores, int64_t* out_ids, void* stream) {
   if (num_lists <= 0 || batch < 0 || k_in <= 0 || k_out <= 0 || k_in > kMaxK || k_out > kMaxK)
     return fail(nullptr, MIPS_EINVAL, "mips_merge_topk: bad sizes lists=%d batch=%d k_in=%d k_out=%d", num_lists, batch, k_in, k_out);
   if (batch == 0) return MIPS_OK;
   if (!scores || !ids || !out_scores || !out_ids) return fail(nullptr, MIPS_EINVAL, "mips_merge_topk: NULL pointer");
   DeviceGuard g(device);
   if (!g.ok) return fail(nullptr, MIPS_ECUDA, "cudaSetDevice(%d) failed", device);
-  cudaError_t e = launch_merge(scores, ids, num_lists, static_cast<int64_t>(batch) * k_in, batch, k_in, k_out, out_scores,
+  cudaError_t e = launch_merge(scores, ids, num_lists, score_list_stride, id_list_stride, batch, k_in, k_out, out_scores,
                                out_ids, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(nullptr, MIPS_ECUDA, "merge launch failed: %s", cudaGetErrorString(e));
   return MIPS_OK;
+}
+
+int mips_merge_topk(int device, const float* scores, const int64_t* ids, int num_lists, int batch, int k_in, int k_out,
+                    float* out_scores, int64_t* out_ids, void* stream) {
+  const int64_t stride = static_cast<int64_t>(batch) * k_in;
+  return mips_merge_topk_strided(device, scores, ids, num_lists, stride, stride, batch, k_in, k_out, out_scores, out_ids,
+                                 stream);
 }
 
 int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void* out, void* stream) {

@@ -68,8 +68,9 @@ cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int ba
 cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
                         size_t smem_bytes, cudaStream_t st);
 cudaError_t configure_scan(size_t smem_bytes);
-cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
-                         int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st);
+cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,
+                         int64_t id_list_stride, int batch, int k_in, int k_out, float* out_scores, int64_t* out_ids,
+                         cudaStream_t st);
 cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int cap, int batch, int k,
                           int64_t id_base, int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st);
 cudaError_t configure_merge();

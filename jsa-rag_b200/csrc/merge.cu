@@ -81,7 +81,7 @@ __device__ __forceinline__ Cand load_cand(const float* s, const int64_t* ids, in
 template <int kMergeE>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int num_lists,
-                  int64_t list_stride, int k_in, int k_out, float* __restrict__ out_scores,
+                  int64_t list_stride, int64_t id_list_stride, int k_in, int k_out, float* __restrict__ out_scores,
                   int64_t* __restrict__ out_ids) {
   constexpr int kMergeKP = 32 * kMergeE;
   extern __shared__ __align__(16) uint8_t merge_smem[];
@@ -98,7 +98,7 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   bool first = true;
   for (int l = warp; l < num_lists; l += kMergeWarps) {
     const float* s = scores + l * list_stride + static_cast<int64_t>(q) * k_in;
-    const int64_t* id = ids + l * list_stride + static_cast<int64_t>(q) * k_in;
+    const int64_t* id = ids + l * id_list_stride + static_cast<int64_t>(q) * k_in;
     if (first) {
 #pragma unroll
       for (int e = 0; e < kMergeE; ++e) acc[e] = load_cand(s, id, lane * kMergeE + e, k_in);
@@ -508,11 +508,12 @@ cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lis
 }
 
 template <int E>
-static cudaError_t launch_merge_e(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
-                                  int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+static cudaError_t launch_merge_e(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,
+                                  int64_t id_list_stride, int batch, int k_in, int k_out, float* out_scores,
+                                  int64_t* out_ids, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(kMergeWarps) * 32 * E * (sizeof(int64_t) + sizeof(uint32_t));
-  merge_topk_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(scores, ids, num_lists, list_stride, k_in, k_out,
-                                                             out_scores, out_ids);
+  merge_topk_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(scores, ids, num_lists, list_stride, id_list_stride, k_in,
+                                                             k_out, out_scores, out_ids);
   return cudaGetLastError();
 }
 
@@ -521,15 +522,18 @@ cudaError_t configure_merge() {
                               kMergeWarps * kMaxK * static_cast<int>(sizeof(int64_t) + sizeof(uint32_t)));
 }
 
-cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride, int batch,
-                         int k_in, int k_out, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,
+                         int64_t id_list_stride, int batch, int k_in, int k_out, float* out_scores, int64_t* out_ids,
+                         cudaStream_t st) {
   if (batch == 0) return cudaSuccess;
   const int kk = k_in > k_out ? k_in : k_out;
   if (kk <= kSmallK)
-    return launch_merge_e<kSmallK / 32>(scores, ids, num_lists, list_stride, batch, k_in, k_out, out_scores, out_ids, st);
+    return launch_merge_e<kSmallK / 32>(scores, ids, num_lists, list_stride, id_list_stride, batch, k_in, k_out,
+                                        out_scores, out_ids, st);
   static cudaError_t cfg = configure_merge();
   if (cfg != cudaSuccess) return cfg;
-  return launch_merge_e<kMaxK / 32>(scores, ids, num_lists, list_stride, batch, k_in, k_out, out_scores, out_ids, st);
+  return launch_merge_e<kMaxK / 32>(scores, ids, num_lists, list_stride, id_list_stride, batch, k_in, k_out, out_scores,
+                                    out_ids, st);
 }
 
 }  // namespace mips

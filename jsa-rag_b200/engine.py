@@ -150,6 +150,35 @@ class MipsEngine:
         return out
 
 
+def packed_result_buffer(batch: int, k: int, device, lists: int = 1):
+    """One byte buffer per list laid out [fp32 scores [B,k] | pad to 8 B | int64 ids [B,k]] plus the two
+    views into it.  A rank's search writes through the views; all ranks' buffers are exchanged with ONE
+    all_gather and merged in place by ``merge_packed`` (no packing kernels)."""
+    s_bytes = (batch * k * 4 + 7) // 8 * 8
+    block = s_bytes + batch * k * 8
+    buf = torch.empty((lists, block), dtype=torch.uint8, device=device)
+    scores = buf[:, :batch * k * 4].view(torch.float32).view(lists, batch, k)
+    ids = buf[:, s_bytes:].view(torch.int64).view(lists, batch, k)
+    return buf, scores, ids
+
+
+def merge_packed(buf: torch.Tensor, batch: int, k_in: int, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merges the [W, block] buffer produced by all-gathering ``packed_result_buffer`` blocks."""
+    lib = N.load()
+    if not buf.is_cuda:
+        raise RuntimeError("merge_packed needs CUDA tensors; there is no CPU fallback")
+    lists, block = buf.shape
+    s_bytes = (batch * k_in * 4 + 7) // 8 * 8
+    out_s = torch.empty((batch, k_out), dtype=torch.float32, device=buf.device)
+    out_i = torch.empty((batch, k_out), dtype=torch.int64, device=buf.device)
+    rc = lib.mips_merge_topk_strided(buf.device.index or 0, ctypes.c_void_p(buf.data_ptr()),
+                                     ctypes.c_void_p(buf.data_ptr() + s_bytes), lists, block // 4, block // 8, batch, k_in,
+                                     int(k_out), ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
+                                     _stream_ptr(buf.device))
+    N.check(rc, None, "mips_merge_topk_strided")
+    return out_s, out_i
+
+
 def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Device-side L-way merge of sorted (score, id) lists: replaces src/index.py:135-157."""
     lib = N.load()

@@ -205,9 +205,23 @@ class B200Index(object):
             return (torch.empty(0, topk, device=queries.device),
                     torch.empty(0, topk, dtype=torch.int64, device=queries.device))
         self._any_rank_has_queries = True
-        ls, li = self._local_search(allqueries, topk, normalize)                   # src/index.py:132
-        gs, gi = dist_utils.all_gather_candidates(ls, li)                          # replaces :139-142
-        ms, mi = self._merge_lists(gs, gi, topk)                                   # replaces :143-157
+        if allqueries.is_cuda and type(self)._local_search is B200Index._local_search:
+            # device path: the local result is written straight into this rank's block of the exchange
+            # buffer; ONE all-gather moves 12*B*k bytes per rank; the merge reads the gathered blocks
+            from .engine import merge_packed, packed_result_buffer
+            bt = int(allqueries.shape[0])
+            buf, ls, li = packed_result_buffer(bt, topk, allqueries.device)
+            n_local = 0 if self._store is None else int(self._store.shape[0])
+            if topk > n_local:
+                raise RuntimeError("selected index k out of range")
+            self._get_engine().search(allqueries, topk, normalize=normalize, out=(ls[0], li[0]))   # src/index.py:132
+            gathered = torch.empty((w, buf.shape[1]), dtype=torch.uint8, device=buf.device)
+            torch.distributed.all_gather_into_tensor(gathered, buf[0])                             # replaces :139-142
+            ms, mi = merge_packed(gathered, bt, topk, topk)                                          # replaces :143-157
+        else:
+            ls, li = self._local_search(allqueries, topk, normalize)               # src/index.py:132
+            gs, gi = dist_utils.all_gather_candidates(ls, li)                      # replaces :139-142
+            ms, mi = self._merge_lists(gs, gi, topk)                               # replaces :143-157
         sl = slice(int(offs[r]), int(offs[r + 1]))
         self._last_all = (mi, offs)
         return ms[sl], mi[sl]

@@ -9,6 +9,7 @@ import sys as _sys
 from . import _native, dist_utils  # noqa: F401
 from .index import B200Index, B200IndexWithEmbeddings, EMBEDDINGS_DIM  # noqa: F401
 from .index_io import load_or_initialize_index, load_passages, save_embeddings_and_index  # noqa: F401
+from .filtering import filter_results_by_id  # noqa: F401
 
 
 def __getattr__(name):  # lazy: engine imports need the CUDA extension

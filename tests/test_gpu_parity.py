@@ -304,3 +304,32 @@ def test_properties_at_full_size(eng, dev):
     if free < 70 * (1 << 30):
         pytest.skip("not enough free device memory for the 33M x 768 index")
     _properties(eng, dev, 33_000_000, 64, 100, 9)
+
+
+def test_raw_c_abi_with_caller_workspace(eng, dev):
+    """The boundary exactly as INTEGRATION.md binds it: plain pointers, caller-owned workspace."""
+    import ctypes
+    lib = eng._native.load()
+    e, q = _synth(30000, 768, 70, 4, dev)
+    h = ctypes.c_void_p()
+    assert lib.mips_create(ctypes.byref(h), 0, 768, 0) == 0
+    try:
+        assert lib.mips_bind_index(h, ctypes.c_void_p(e.data_ptr()), e.shape[0], e.stride(0), 5, 3) == 0
+        need = ctypes.c_size_t(0)
+        assert lib.mips_workspace_bytes(h, 70, 50, ctypes.byref(need)) == 0 and need.value > 0
+        ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 1024
+        s = torch.empty(70, 50, device=dev)
+        i = torch.empty(70, 50, dtype=torch.int64, device=dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        args = (h, ctypes.c_void_p(q.data_ptr()), 2, 768, 70, 50, 0, ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(i.data_ptr()))
+        assert lib.mips_search_local(*args, ctypes.c_void_p(ws.data_ptr() + off), need.value, st) == 0
+        rs, ri = _torch_ref(e, q, 50)
+        torch.cuda.synchronize()
+        assert torch.equal(i, ri * 3 + 5) and float((s - rs).abs().max()) < 1e-5
+        assert lib.mips_last_launch_count(h) >= 3
+        # too small a workspace is refused, nothing is launched
+        assert lib.mips_search_local(*args, ctypes.c_void_p(ws.data_ptr() + off), 4096, st) == eng._native.MIPS_EWORKSPACE
+        assert "workspace" in eng._native.last_error(h)
+    finally:
+        lib.mips_destroy(h)

@@ -173,3 +173,16 @@ def test_two_rank_search_over_gloo(mode, tmp_path):
     import torch.multiprocessing as mp
     import _dist_worker
     mp.spawn(_dist_worker.worker, args=(2, _free_port(), str(tmp_path), mode), nprocs=2, join=True)
+
+
+def test_filter_results_by_id(eng):
+    """src/tasks/base.py:96-148: drop the source passage, re-append violators when short, cut to topk."""
+    docs = [[{"id": "a"}, {"id": "b"}, {"id": "c"}, {"id": "d"}], [{"id": "x"}, {"id": "y"}, {"id": "z"}, {"id": "w"}]]
+    scores = [[4.0, 3.0, 2.0, 1.0], [8.0, 7.0, 6.0, 5.0]]
+    meta = [{"id": "b"}, {"id": "none"}]
+    p, s = eng.filter_results_by_id(meta, docs, scores, 2)
+    assert [[d["id"] for d in r] for r in p] == [["a", "c"], ["x", "y"]] and [list(r) for r in s] == [[4.0, 2.0], [8.0, 7.0]]
+    p, s = eng.filter_results_by_id(meta, docs, scores, 4)           # short after filtering: violator appended back
+    assert [d["id"] for d in p[0]] == ["a", "c", "d", "b"] and list(s[0]) == [4.0, 2.0, 1.0, 3.0]
+    p, s = eng.filter_results_by_id(None, docs, scores, 3)           # padding instance: plain cut
+    assert [len(r) for r in p] == [3, 3] and s[1] == [8.0, 7.0, 6.0]

@@ -72,6 +72,14 @@ const char* mips_last_error(const mips_handle* h); /* h may be NULL: message of 
 int mips_bind_index(mips_handle* h, const void* emb, int64_t n_local, int64_t ld,
                     int64_t id_base, int64_t id_stride);
 
+/*
+ * Same, with an explicit storage layout: layout 1 = [n_local, dim] rows (ld >= dim); layout 0 =
+ * [dim, n_local] — the reference's own `.embeddings` layout (src/index.py:52), ld >= n_local — which
+ * is consumed as an MN-major tcgen05 operand straight from the reference-format tensor (zero copy).
+ */
+int mips_bind_index_layout(mips_handle* h, const void* emb, int64_t n_local, int64_t ld, int layout,
+                           int64_t id_base, int64_t id_stride);
+
 /* Bytes of device workspace mips_search_local needs for up to max_batch queries and top max_k. */
 int mips_workspace_bytes(const mips_handle* h, int max_batch, int max_k, size_t* out);
 

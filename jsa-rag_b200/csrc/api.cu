@@ -22,6 +22,7 @@ struct mips_handle {
   // bound index
   const void* emb = nullptr;
   int64_t n_local = 0, ld = 0, id_base = 0, id_stride = 1;
+  int layout = 1;   // 1: [n_local, dim] K-major rows; 0: [dim, n_local] (the reference's layout, MN-major operand)
   CUtensorMap tmap_e;
   bool bound = false;
   // kernel geometry
@@ -104,6 +105,21 @@ int encode_rows_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t r
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->dim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKChunk), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = h->dtype == MIPS_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MIPS_OK;
+}
+
+// Generic row-major [rows, cols] 16-bit matrix -> 2-D tensor map with box {64 cols (128 B), box_rows}.
+int encode_2d_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kKChunk), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
@@ -205,24 +221,36 @@ void mips_destroy(mips_handle* h) {
   delete h;
 }
 
-int mips_bind_index(mips_handle* h, const void* emb, int64_t n_local, int64_t ld, int64_t id_base, int64_t id_stride) {
+int mips_bind_index_layout(mips_handle* h, const void* emb, int64_t n_local, int64_t ld, int layout, int64_t id_base,
+                           int64_t id_stride) {
   if (!h) return MIPS_EINVAL;
+  if (layout != 0 && layout != 1) return fail(h, MIPS_EINVAL, "layout=%d invalid (0 = [dim, n], 1 = [n, dim])", layout);
   if (n_local < 0 || n_local > 0x7FFFFF00ll) return fail(h, MIPS_EINVAL, "n_local=%lld out of range", (long long)n_local);
   if (n_local > 0 && !emb) return fail(h, MIPS_EINVAL, "emb is NULL");
-  if (ld < h->dim || (ld * 2) % 16 != 0) return fail(h, MIPS_EINVAL, "row stride ld=%lld must be >= dim and 16-byte aligned", (long long)ld);
+  const int64_t min_ld = layout == 1 ? h->dim : n_local;
+  if (ld < min_ld || (ld * 2) % 16 != 0)
+    return fail(h, MIPS_EINVAL, "row stride ld=%lld must be >= %lld and 16-byte aligned", (long long)ld, (long long)min_ld);
   if (reinterpret_cast<uintptr_t>(emb) % 16 != 0) return fail(h, MIPS_EINVAL, "emb must be 16-byte aligned");
   h->emb = emb;
   h->n_local = n_local;
   h->ld = ld;
+  h->layout = layout;
   h->id_base = id_base;
   h->id_stride = id_stride;
   h->bound = false;
   if (n_local > 0) {
-    int rc = encode_rows_map(h, &h->tmap_e, emb, n_local, ld, kTileN);
+    // [n, dim]: box = 64 passages x 64 dims, rows are passages (K-major B operand)
+    // [dim, n]: box = 64 dims x 64 passages, rows are dims   (MN-major B operand, no transpose needed)
+    int rc = layout == 1 ? encode_2d_map(h, &h->tmap_e, emb, n_local, h->dim, ld, kTileN)
+                         : encode_2d_map(h, &h->tmap_e, emb, h->dim, n_local, ld, kKChunk);
     if (rc != MIPS_OK) return rc;
   }
   h->bound = true;
   return MIPS_OK;
+}
+
+int mips_bind_index(mips_handle* h, const void* emb, int64_t n_local, int64_t ld, int64_t id_base, int64_t id_stride) {
+  return mips_bind_index_layout(h, emb, n_local, ld, 1, id_base, id_stride);
 }
 
 int mips_workspace_bytes(const mips_handle* h, int max_batch, int max_k, size_t* out) {
@@ -282,7 +310,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   p.num_stages = h->num_stages;
   p.chunks_per_stage = h->chunks_per_stage;
   p.k = k;
-  p.idesc = ptx::make_idesc_f16(kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
+  p.b_mn = h->layout == 0 ? 1 : 0;
   p.dim = h->dim;
   p.qbuf = qbuf;
   p.cap = k <= kSmallK ? kCap : kCapBig;
@@ -326,7 +354,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     p.q_row0 = q0;
     p.seed = nullptr;
     p.m64 = (p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
-    p.idesc = ptx::make_idesc_f16(p.m64 ? 64 : kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0);
+    p.idesc = ptx::make_idesc_f16(p.m64 ? 64 : kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0) |
+              (p.b_mn ? (1u << 16) : 0u);   // bit 16: B operand is MN-major
     for (int lv = 0; lv < n_levels; ++lv) {
       ScanParams pp = p;
       pp.num_tiles = levels[lv] * grid < num_tiles ? levels[lv] * grid : num_tiles;
@@ -374,7 +403,7 @@ int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void*
   if (!h->bound) return fail(h, MIPS_ENOTBOUND, "mips_bind_index has not been called");
   if (n < 0 || (n > 0 && (!local_rows || !out))) return fail(h, MIPS_EINVAL, "bad gather arguments");
   DeviceGuard g(h->device);
-  CUDA_TRY(h, launch_gather_rows(h->emb, h->ld, h->dim, h->n_local, local_rows, n, out, static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(h, launch_gather_rows(h->emb, h->ld, h->dim, h->n_local, h->layout, local_rows, n, out, static_cast<cudaStream_t>(stream)));
   return MIPS_OK;
 }
 

@@ -40,6 +40,7 @@ struct ScanParams {
   int k;                 // top-k (<= kMaxK)
   int batch;             // valid queries in this pass (<= kNQ)
   int m64;               // 1: UMMA M=64 (batch <= 64), 0: UMMA M=128
+  int b_mn;              // 1: index stored [dim, n_local] (MN-major B operand), 0: [n_local, dim] (K-major)
   int q_row0;            // first row of this pass in the prepared query buffer
   int dim;               // embedding dimension
   const void* qbuf;      // prepared queries [batch_pad, dim] in the index dtype (row-major, zero padded)
@@ -74,8 +75,8 @@ cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists,
 cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int cap, int batch, int k,
                           int64_t id_base, int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st);
 cudaError_t configure_merge();
-cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, const int64_t* rows, int64_t n,
-                               void* out, cudaStream_t st);
+cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, int layout, const int64_t* rows,
+                               int64_t n, void* out, cudaStream_t st);
 
 // ---- order-preserving float <-> uint32 (larger float -> larger uint) ----
 __host__ __device__ inline uint32_t f32_to_ord(float f) {

@@ -271,9 +271,12 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
           const int kc0 = si * cps;
           const int nch = nk - kc0 < cps ? nk - kc0 : cps;
           ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, nch * kChunkBytes);
-          for (int c = 0; c < nch; ++c)
+          for (int c = 0; c < nch; ++c) {
+            // tensor-map coordinates are (inner, outer): (dim, passage) for [n, dim], (passage, dim) for [dim, n]
+            const int c_dim = (kc0 + c) * kKChunk, c_row = t * kTileN;
             ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * stage_bytes + c * kChunkBytes,
-                             (kc0 + c) * kKChunk, t * kTileN, ptx::kEvictFirst);
+                             p.b_mn ? c_row : c_dim, p.b_mn ? c_dim : c_row, ptx::kEvictFirst);
+          }
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -311,19 +314,22 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
             const int nch = nk - kc0 < cps ? nk - kc0 : cps;
             for (int c = 0; c < nch; ++c) {
               const int kc = kc0 + c;
-              // B: 64 passages x 64 el, K-major SWIZZLE_128B; +32 B (= +2 in the descriptor) per K=16 step
+              // B: 64 passages x 64 el, SWIZZLE_128B.  K-major ([n, dim] index): rows are passages, a K=16
+              // step advances 32 B inside the swizzle row (+2 in the 16-byte-granular address field).
+              // MN-major ([dim, n] index): rows are dims, a K=16 step advances 16 rows = 2048 B (+128).
               const uint64_t db = ptx::make_kmajor_sw128_desc(st_smem + stage * stage_bytes + c * kChunkBytes);
+              const uint32_t bstep = p.b_mn ? 128u : 2u;
               if (kc < nk_ts) {
                 // A from TMEM: 8 columns (16 packed 16-bit values per lane) per K=16 step
                 const uint32_t a_tmem = tmem_base + kc * (kKChunk / 2);
 #pragma unroll
                 for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
-                  ptx::umma_f16_ts(d_tmem, a_tmem + 8 * k4, db + 2 * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+                  ptx::umma_f16_ts(d_tmem, a_tmem + 8 * k4, db + bstep * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
               } else {
                 const uint64_t da = ptx::make_kmajor_sw128_desc(q_smem + (kc - nk_ts) * kQChunkBytes);
 #pragma unroll
                 for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
-                  ptx::umma_f16(d_tmem, da + 2 * k4, db + 2 * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
+                  ptx::umma_f16(d_tmem, da + 2 * k4, db + bstep * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
               }
             }
             ptx::umma_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs retire
@@ -592,22 +598,26 @@ cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int ba
 // ------------------------------------------------------------------------------------------------
 // Row gather for the 3-tuple search_knn variant (build_server/index.py:228-229).
 // ------------------------------------------------------------------------------------------------
-__global__ void gather_rows_kernel(const uint16_t* __restrict__ emb, int64_t ld, int dim, int64_t n_local,
+__global__ void gather_rows_kernel(const uint16_t* __restrict__ emb, int64_t ld, int dim, int64_t n_local, int layout,
                                    const int64_t* __restrict__ rows, int64_t n, uint16_t* __restrict__ out) {
   const int64_t i = blockIdx.x;
   if (i >= n) return;
   const int64_t r = rows[i];
   const bool ok = r >= 0 && r < n_local;
-  const int vec = dim / 8;  // dim % 64 == 0 -> 16-byte vectors
-  const uint4* src = reinterpret_cast<const uint4*>(emb + r * ld);
-  uint4* dst = reinterpret_cast<uint4*>(out + i * dim);
-  for (int c = threadIdx.x; c < vec; c += blockDim.x) dst[c] = ok ? src[c] : make_uint4(0, 0, 0, 0);
+  if (layout == 1) {
+    const int vec = dim / 8;  // dim % 64 == 0 -> 16-byte vectors
+    const uint4* src = reinterpret_cast<const uint4*>(emb + r * ld);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * dim);
+    for (int c = threadIdx.x; c < vec; c += blockDim.x) dst[c] = ok ? src[c] : make_uint4(0, 0, 0, 0);
+  } else {  // [dim, n]: column gather
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) out[i * dim + c] = ok ? emb[static_cast<int64_t>(c) * ld + r] : 0;
+  }
 }
 
-cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, const int64_t* rows, int64_t n,
-                               void* out, cudaStream_t st) {
+cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, int layout, const int64_t* rows,
+                               int64_t n, void* out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  gather_rows_kernel<<<static_cast<unsigned>(n), 128, 0, st>>>(static_cast<const uint16_t*>(emb), ld, dim, n_local,
+  gather_rows_kernel<<<static_cast<unsigned>(n), 128, 0, st>>>(static_cast<const uint16_t*>(emb), ld, dim, n_local, layout,
                                                                rows, n, static_cast<uint16_t*>(out));
   return cudaGetLastError();
 }

@@ -51,14 +51,22 @@ class MipsEngine:
 
     # ------------------------------------------------------------------ index binding
     def bind(self, store: torch.Tensor, id_base: int = 0, id_stride: int = 1) -> None:
-        """``store``: [n_local, dim] K-major CUDA tensor (row stride may exceed dim)."""
-        if store.dim() != 2 or store.shape[1] != self.dim or store.stride(1) != 1:
-            raise ValueError(f"store must be [n, {self.dim}] with unit inner stride, got {tuple(store.shape)} / {store.stride()}")
+        """``store``: [n_local, dim] CUDA tensor.  Rows contiguous (K-major, row stride may exceed dim) or
+        the transposed view of a reference-layout [dim, n_local] tensor (columns contiguous): both are
+        consumed in place, the latter as an MN-major tensor-core operand."""
+        if store.dim() != 2 or store.shape[1] != self.dim:
+            raise ValueError(f"store must be [n, {self.dim}], got {tuple(store.shape)}")
         if store.dtype != self.dtype or store.device != self.device:
             raise ValueError(f"store must be {self.dtype} on {self.device}")
-        ld = store.stride(0) if store.shape[0] > 1 else self.dim
-        N.check(self._lib.mips_bind_index(self._h, ctypes.c_void_p(store.data_ptr()), store.shape[0], ld,
-                                          int(id_base), int(id_stride)), self._h, "mips_bind_index")
+        n = int(store.shape[0])
+        if store.stride(1) == 1 or n <= 1 and store.is_contiguous():
+            layout, ld = 1, (store.stride(0) if n > 1 else self.dim)
+        elif store.stride(0) == 1:
+            layout, ld = 0, store.stride(1)           # [dim, n] storage seen through .t()
+        else:
+            raise ValueError(f"store needs unit stride along rows or columns, got strides {store.stride()}")
+        N.check(self._lib.mips_bind_index_layout(self._h, ctypes.c_void_p(store.data_ptr()), n, ld, layout,
+                                                 int(id_base), int(id_stride)), self._h, "mips_bind_index")
         self._store = store  # keep alive: the extension only borrows the pointer
 
     @property

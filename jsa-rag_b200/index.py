@@ -30,8 +30,15 @@ EMBEDDINGS_DIM: int = 768  # reference src/retrievers.py:14
 
 
 class B200Index(object):
-    def __init__(self, dtype: torch.dtype = torch.float16, device: Optional[str] = None):
-        self._store: Optional[torch.Tensor] = None  # [n_local, dim] K-major
+    def __init__(self, dtype: torch.dtype = torch.float16, device: Optional[str] = None, layout: str = "nd"):
+        """``layout``: physical storage of the matrix.  "nd" (default) = one contiguous row per passage
+        (K-major; streams at full HBM bandwidth).  "dn" = the reference's own contiguous [dim, n_local]
+        layout (src/index.py:52), searched in place as an MN-major tensor-core operand (~0.6x the
+        bandwidth: a passage tile then touches dim separate DRAM pages); n_local should be a multiple of 8."""
+        if layout not in ("nd", "dn"):
+            raise ValueError("layout must be 'nd' or 'dn'")
+        self.layout = layout
+        self._store: Optional[torch.Tensor] = None  # [n_local, dim] (a transposed view when layout == "dn")
         self.doc_map = dict()
         self.is_in_gpu = True  # reference attribute (src/index.py:48); False keeps storage on the host (I/O only)
         self.dtype = dtype
@@ -70,14 +77,21 @@ class B200Index(object):
             return
         if value.dim() != 2:
             raise ValueError("embeddings must be [dim, n]")
-        self._store = value.t().to(device=self._storage_device(), dtype=self.dtype).contiguous()
+        value = value.to(device=self._storage_device(), dtype=self.dtype)
+        self._store = value.contiguous().t() if self.layout == "dn" else value.t().contiguous()
 
     def init_embeddings(self, passages, dim: Optional[int] = EMBEDDINGS_DIM):
         """src/index.py:50-54 — allocates zeroed storage; passages were round-robin sharded by
         load_passages (src/index_io.py:41), hence global id = local * W + rank."""
         self.doc_map = {i: doc for i, doc in enumerate(passages)}
-        self._store = torch.zeros(len(passages), dim, dtype=self.dtype, device=self._storage_device())
+        self._store = self._alloc(len(passages), dim, zero=True)
         self._set_sharding("round_robin")
+
+    def _alloc(self, n: int, dim: int, zero: bool = False) -> torch.Tensor:
+        make = torch.zeros if zero else torch.empty
+        if self.layout == "dn":
+            return make(dim, n, dtype=self.dtype, device=self._storage_device()).t()
+        return make(n, dim, dtype=self.dtype, device=self._storage_device())
 
     def _set_sharding(self, mode: str) -> None:
         self._sharding = mode
@@ -147,7 +161,7 @@ class B200Index(object):
                 n_passages += 1
         dim = shards[0].shape[0] if shards else EMBEDDINGS_DIM
         n = sum(int(s.shape[1]) for s in shards)
-        self._store = torch.empty(n, dim, dtype=self.dtype, device=self._storage_device())
+        self._store = self._alloc(n, dim)
         at = 0
         for s in shards:
             self._store[at:at + s.shape[1]].copy_(s.t())
@@ -193,6 +207,8 @@ class B200Index(object):
         """
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
         self._any_rank_has_queries = False
+        if self._store is not None and self._store.is_cuda and queries.device != self._store.device:
+            queries = queries.to(self._store.device)
         if w == 1:
             if queries.shape[0] == 0:
                 dev = queries.device

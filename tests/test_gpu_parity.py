@@ -355,3 +355,10 @@ def test_reference_layout_is_consumed_in_place(eng, dev, n, d, b, k, dtype):
     s2, i2 = m_mn.search(q, k)
     assert torch.equal(i1, i2) and torch.equal(s1, s2)
     assert torch.equal(m_mn.gather_rows(i2[:, :2]), e[i2[:, :2].reshape(-1)])
+    if n % 8 == 0 or n == 5000:
+        idx = eng.B200Index(dtype=dtype, layout="dn")            # drop-in object storing the reference layout
+        idx.init_embeddings([{"id": str(j)} for j in range(n)], dim=d)
+        idx.embeddings[:, :] = e.T
+        assert idx.embeddings.is_contiguous()
+        s3, i3 = idx.search(q, k)
+        assert torch.equal(i3, i1) and torch.equal(s3, s1)

@@ -78,6 +78,24 @@ def test_storage_is_reference_shaped_view(eng):
     assert tuple(idx._store.shape) == (12, 768)
 
 
+def test_reference_layout_storage_option(eng, tmp_path):
+    """layout="dn": `.embeddings` is a real contiguous [dim, n] tensor like the reference's; same files on disk."""
+    idx = eng.B200Index(device="cpu", layout="dn")
+    idx.init_embeddings([{"id": str(i)} for i in range(24)], dim=768)
+    assert idx.embeddings.is_contiguous() and tuple(idx.embeddings.shape) == (768, 24) and tuple(idx._store.shape) == (24, 768)
+    x = torch.randn(24, 768)
+    idx.embeddings[:, :] = x.T
+    assert torch.equal(idx._store, x.half())
+    idx.save_index(str(tmp_path), 2)
+    a = eng.B200Index(device="cpu")
+    a.load_index(str(tmp_path), 2)
+    b = eng.B200Index(device="cpu", layout="dn")
+    b.load_index(str(tmp_path), 2)
+    assert torch.equal(a._store, x.half()) and torch.equal(b._store, x.half()) and b.embeddings.is_contiguous()
+    b.embeddings = torch.randn(768, 8)
+    assert b.embeddings.is_contiguous() and tuple(b._store.shape) == (8, 768)
+
+
 def test_shard_files_match_reference_format(eng, tmp_path):
     g = load_golden("flat_n1003_d768_b8_k20")
     n = int(g["n"])

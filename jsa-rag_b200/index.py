@@ -242,6 +242,38 @@ class B200Index(object):
         self._last_all = (mi, offs)
         return ms[sl], mi[sl]
 
+    def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
+        """Captures one distributed search (query all-gather, fused scan + select, candidate all-gather,
+        merge) for a fixed per-rank batch into a CUDA graph.  Returns ``run(queries) -> (scores, ids)``
+        that copies the queries into the captured input and replays the graph: ~10 us of host time per
+        search instead of ~100 us, which matters when a search lasts ~1 ms (8-way sharded index).
+        All ranks must call this together; ``equal_batch`` is implied."""
+        if self._store is None or not self._store.is_cuda:
+            raise RuntimeError("make_graphed_search needs the index on a CUDA device; there is no CPU fallback")
+        dev = self._store.device
+        prev_equal = self.equal_batch
+        self.equal_batch = True
+        static_q = torch.zeros(batch, int(self._store.shape[1]), dtype=query_dtype, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):                      # warm-up: workspace growth, NCCL channels, lazy inits
+                self.search(static_q, topk, normalize)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out_s, out_i = self.search(static_q, topk, normalize)
+        self.equal_batch = prev_equal
+
+        def run(queries: torch.Tensor):
+            static_q.copy_(queries, non_blocking=True)
+            graph.replay()
+            return out_s, out_i
+
+        run.graph, run.static_input, run.outputs = graph, static_q, (out_s, out_i)
+        return run
+
     # ------------------------------------------------------------------ passage resolution
     def _owner_and_local(self, gids: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         w = dist_utils.get_world_size()

@@ -243,13 +243,14 @@ class B200Index(object):
         return ms[sl], mi[sl]
 
     def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
-        """Captures one distributed search (query all-gather, fused scan + select, candidate all-gather,
-        merge) for a fixed per-rank batch into a CUDA graph.  Returns ``run(queries) -> (scores, ids)``
-        that copies the queries into the captured input and replays the graph: ~10 us of host time per
-        search instead of ~100 us, which matters when a search lasts ~1 ms (8-way sharded index).
-        All ranks must call this together; ``equal_batch`` is implied."""
+        """Captures one single-rank search (prep, seeded pre-passes, fused scan, select) for a fixed batch
+        into a CUDA graph.  Returns ``run(queries) -> (scores, ids)`` that copies the queries into the
+        captured input and replays the graph (~2 us of host time per search instead of ~40 us).
+        Multi-rank capture (NCCL collectives inside the graph) hung in testing and is refused."""
         if self._store is None or not self._store.is_cuda:
             raise RuntimeError("make_graphed_search needs the index on a CUDA device; there is no CPU fallback")
+        if dist_utils.get_world_size() > 1:
+            raise NotImplementedError("graph capture of the distributed search is not supported yet")
         dev = self._store.device
         prev_equal = self.equal_batch
         self.equal_batch = True

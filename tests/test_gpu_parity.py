@@ -362,3 +362,19 @@ def test_reference_layout_is_consumed_in_place(eng, dev, n, d, b, k, dtype):
         assert idx.embeddings.is_contiguous()
         s3, i3 = idx.search(q, k)
         assert torch.equal(i3, i1) and torch.equal(s3, s1)
+
+
+def test_cuda_graph_replay_of_a_search(eng, dev):
+    e, q = _synth(300_000, 768, 64, 17, dev)
+    idx = eng.B200Index()
+    idx._store = e
+    idx._set_sharding("round_robin")
+    run = idx.make_graphed_search(64, 100)
+    s0, i0 = idx.search(q, 100)
+    s1, i1 = run(q)
+    torch.cuda.synchronize()
+    assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    q2 = torch.roll(q, 1, 0)
+    s2, i2 = run(q2)
+    torch.cuda.synchronize()
+    assert torch.equal(i2, torch.roll(i0, 1, 0))

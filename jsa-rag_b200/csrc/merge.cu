@@ -1,14 +1,16 @@
-// Second-stage top-k merge: reduces L sorted candidate lists per query to one sorted top-k.
+// Selection and merge kernels that follow the fused scan.
 //
-// Used twice: (1) per shard, over the per-CTA partial lists the scan kernel emits (L = #CTAs);
-// (2) across ranks, over the all-gathered per-rank results (L = world size) — this replaces the
-// 2*W gathers + concat + second torch.topk of the reference (src/index.py:135-157).
-//
-// One CTA per query, 8 warps.  Each warp folds its share of the lists into a register-resident
-// sorted list of KP = 32*E entries with the bitonic merge step
-//     C[i] = better(A[i], B[KP-1-i])   (C is bitonic and holds the top KP of A u B)
-// followed by log2(KP) compare-exchange stages; the 8 warp results are folded by warp 0 through
-// shared memory.  Order: score descending, id ascending on equal scores (total, deterministic).
+//  * select_topk_kernel / select_topk_big_kernel — per shard: exact top-k of the (unsorted) candidate
+//    lists the scan's CTAs leave in the workspace (k <= 128: score words in registers; k <= 1024:
+//    streamed from L2).  MSB-first bisection with block-wide counts, then rank-by-counting.
+//  * merge_topk_kernel — across ranks: L sorted (fp32 score, int64 id) lists per query, as produced by
+//    all-gathering every rank's result, are reduced to one sorted top-k.  This replaces the 2*W
+//    gathers + concat + second torch.topk of the reference (src/index.py:135-157).  One CTA per
+//    query, 8 warps: each warp folds its share of the lists into a register-resident sorted list of
+//    KP = 32*E entries with the bitonic merge step  C[i] = better(A[i], B[KP-1-i])  (C is bitonic
+//    and holds the top KP of A u B) followed by log2(KP) compare-exchange stages; the 8 warp
+//    results are folded by warp 0 through shared memory.
+// Order everywhere: score descending, id ascending on equal scores (total, deterministic).
 #include "internal.h"
 
 #include <math.h>

@@ -143,8 +143,8 @@ WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
   w.q_off = off;    off += align_up(bpad * h->dim * 2, 1024);
   w.cand_off = off; off += align_up(grid * kNQ * cap * sizeof(uint64_t), 1024);
   w.pk_off = off;   off += align_up(grid * kNQ * sizeof(int), 1024);
-  w.seed_s_off = off; off += align_up(static_cast<size_t>(kNQ) * max_k * sizeof(float), 1024);
-  w.seed_i_off = off; off += align_up(static_cast<size_t>(kNQ) * max_k * sizeof(int64_t), 1024);
+  w.seed_s_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * max_k * sizeof(float), 1024);
+  w.seed_i_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * max_k * sizeof(int64_t), 1024);
   w.total = off;
   return w;
 }
@@ -327,51 +327,70 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   // ~k * tiles / (grid * sample_tiles) candidates per (CTA, query): few enough that no list is ever
   // compacted in-stream and the select kernel takes the raw lists.  levels[] holds the tiles per CTA
   // of each pre-pass (the first is unseeded and one tile deep, so its lists hold <= 128 entries).
-  const int tiles_per_cta = (num_tiles + grid - 1) / grid;
-  int levels[6];
-  int n_levels = 0;
-  if (tiles_per_cta > p.emit / kTileN && !(h->dbg_flags & kDbgNoSeed)) {   // longer unseeded scans would overflow `emit`
-    // target appended candidates per (CTA, query): ~150 for the 512-slot lists, ~1200 for the 2048-slot ones
-    const int64_t denom = static_cast<int64_t>(grid) * (k <= kSmallK ? 150 : 1200);
-    int64_t need = tiles_per_cta;
-    int tmp[6];
-    int nt = 0;
-    while (nt < 6) {
-      int64_t nxt = (need * k + denom - 1) / denom;
-      if (nxt < 1) nxt = 1;
-      if (nxt >= need) break;
-      tmp[nt++] = static_cast<int>(nxt);
-      need = nxt;
-      if (nxt <= p.emit / kTileN) break;   // an unseeded pass this short leaves <= emit candidates per list
-    }
-    for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
-  }
   float* seed_scores = reinterpret_cast<float*>(ws + w.seed_s_off);
   int64_t* seed_ids = reinterpret_cast<int64_t*>(ws + w.seed_i_off);
 
-  for (int q0 = 0; q0 < batch; q0 += kNQ) {
-    p.batch = batch - q0 < kNQ ? batch - q0 : kNQ;
+  // Queries are processed in launches of up to kMaxBlocks blocks of kNQ (128) queries.  With nblk > 1
+  // blocks per launch the CTAs split into nblk groups that scan the same tile sequence side by side
+  // (one HBM read feeds nblk blocks through the L2), which moves large batches from HBM-bound passes
+  // towards the tensor-core bound.
+  constexpr int kMaxBlocks = 4;
+  for (int q0 = 0; q0 < batch;) {
+    int nblk = (batch - q0 + kNQ - 1) / kNQ;
+    if (nblk > kMaxBlocks) nblk = kMaxBlocks;
+    if (nblk == 3) nblk = 2;                       // grid (148) must divide evenly
+    if (h->dbg_flags & kDbgOneBlock) nblk = 1;
+    const int launch_grid = grid >= nblk ? (grid / nblk) * nblk : nblk;   // tiny indices: surplus CTAs just idle
+    const int nslots = launch_grid / nblk;         // CTAs (= candidate lists) per query block
+    p.nblk = nblk;
+    p.batch = batch - q0 < kNQ * nblk ? batch - q0 : kNQ * nblk;
     p.q_row0 = q0;
     p.seed = nullptr;
-    p.m64 = (p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
+    p.m64 = (nblk == 1 && p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
     p.idesc = ptx::make_idesc_f16(p.m64 ? 64 : kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0) |
               (p.b_mn ? (1u << 16) : 0u);   // bit 16: B operand is MN-major
+
+    // Sampled pre-passes.  The k-th best score of any sample of the shard is a valid lower bound of
+    // the final k-th score, so it can seed the thresholds of a larger pass, which then appends only
+    // ~k * tiles / (lists * sample_tiles) candidates per (CTA, query): few enough that no list is ever
+    // compacted in-stream and the select kernel takes the raw lists.  levels[] holds the tiles per CTA
+    // of each pre-pass (the first is unseeded and short enough to leave <= emit candidates per list).
+    const int tiles_per_cta = (num_tiles + nslots - 1) / nslots;
+    int levels[6];
+    int n_levels = 0;
+    if (tiles_per_cta > p.emit / kTileN && !(h->dbg_flags & kDbgNoSeed)) {   // longer unseeded scans would overflow `emit`
+      // target appended candidates per (CTA, query): ~150 for the 512-slot lists, ~1200 for the 2048-slot ones
+      const int64_t denom = static_cast<int64_t>(nslots) * (k <= kSmallK ? 150 : 1200);
+      int64_t need = tiles_per_cta;
+      int tmp[6];
+      int nt = 0;
+      while (nt < 6) {
+        int64_t nxt = (need * k + denom - 1) / denom;
+        if (nxt < 1) nxt = 1;
+        if (nxt >= need) break;
+        tmp[nt++] = static_cast<int>(nxt);
+        need = nxt;
+        if (nxt <= p.emit / kTileN) break;   // an unseeded pass this short leaves <= emit candidates per list
+      }
+      for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
+    }
     for (int lv = 0; lv < n_levels; ++lv) {
       ScanParams pp = p;
-      pp.num_tiles = levels[lv] * grid < num_tiles ? levels[lv] * grid : num_tiles;
+      pp.num_tiles = levels[lv] * nslots < num_tiles ? levels[lv] * nslots : num_tiles;
       pp.stats = nullptr;
-      CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, pp, grid, h->smem_bytes, st));
-      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.cap, p.batch, k, 0, 1, seed_scores, seed_ids, st));
+      CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, pp, launch_grid, h->smem_bytes, st));
+      CUDA_TRY(h, launch_select(p.cand, p.part_cnt, nslots, nblk, p.cap, p.batch, k, 0, 1, seed_scores, seed_ids, st));
       h->last_launches += 2;
       p.seed = seed_scores;
     }
     const bool timed = (h->dbg_flags & kDbgTimeScan) && h->timing_ready && h->n_timed < mips_handle::kMaxTimed;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev0[h->n_timed], st));
-    CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, grid, h->smem_bytes, st));
+    CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, launch_grid, h->smem_bytes, st));
     if (timed) { CUDA_TRY(h, cudaEventRecord(h->ev1[h->n_timed], st)); h->n_timed++; }
-    CUDA_TRY(h, launch_select(p.cand, p.part_cnt, grid, p.cap, p.batch, k, h->id_base, h->id_stride,
+    CUDA_TRY(h, launch_select(p.cand, p.part_cnt, nslots, nblk, p.cap, p.batch, k, h->id_base, h->id_stride,
                               out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
     h->last_launches += 2;
+    q0 += p.batch;
   }
   return MIPS_OK;
 }

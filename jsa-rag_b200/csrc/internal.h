@@ -38,7 +38,8 @@ struct ScanParams {
   int num_stages;        // pipeline depth that fits next to the resident queries
   int chunks_per_stage;  // K chunks (8 KiB each) one pipeline stage carries
   int k;                 // top-k (<= kMaxK)
-  int batch;             // valid queries in this pass (<= kNQ)
+  int batch;             // valid queries in this launch (<= kNQ * nblk)
+  int nblk;              // query blocks scanned concurrently by this launch (1, 2 or 4; grid % nblk == 0)
   int m64;               // 1: UMMA M=64 (batch <= 64), 0: UMMA M=128
   int b_mn;              // 1: index stored [dim, n_local] (MN-major B operand), 0: [n_local, dim] (K-major)
   int q_row0;            // first row of this pass in the prepared query buffer
@@ -59,6 +60,7 @@ constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + s
 constexpr int kDbgNoMma = 2;     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
 constexpr int kDbgNoSeed = 4;    // disable the sampled pre-passes (thresholds start at -inf)
 constexpr int kDbgForceM128 = 16; // always use UMMA M=128 (A/B test of the M=64 small-batch mode)
+constexpr int kDbgOneBlock = 32;  // one query block per launch even for large batches (A/B test of the L2-shared multi-block scan)
 constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };
@@ -72,7 +74,7 @@ cudaError_t configure_scan(size_t smem_bytes);
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,
                          int64_t id_list_stride, int batch, int k_in, int k_out, float* out_scores, int64_t* out_ids,
                          cudaStream_t st);
-cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int cap, int batch, int k,
+cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int nblk, int cap, int batch, int k,
                           int64_t id_base, int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st);
 cudaError_t configure_merge();
 cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, int layout, const int64_t* rows,

@@ -225,7 +225,7 @@ __device__ __forceinline__ uint32_t block_bisect(const uint32_t (&v)[NV], int kk
 constexpr int kSelStage2 = kSelThreads;  // survivors of phase 1 are re-bisected one per thread
 
 __global__ void __launch_bounds__(kSelThreads, 1)
-select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int k,
+select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int nblk, int k,
                    int64_t id_base, int64_t id_stride, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_ids) {
   __shared__ int s_cnt[32];
@@ -234,6 +234,8 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
   __shared__ uint64_t s_win[kSmallK];
   __shared__ uint64_t s_key[kSelStage2];
   const int q = blockIdx.x;
+  // query q of the launch lives in query block q / kNQ; its lists are those of CTAs l * nblk + q / kNQ
+  const int qblk = q / kNQ, ql = q % kNQ;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -251,9 +253,10 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
 #pragma unroll
   for (int i = 0; i < kSelListsPerWarp; ++i) {
     const int l = warp + i * kSelWarps;
-    int c = l < num_lists ? part_cnt[l * kNQ + q] : 0;
+    const size_t cta = static_cast<size_t>(l < num_lists ? l : 0) * nblk + qblk;
+    int c = l < num_lists ? part_cnt[cta * kNQ + ql] : 0;
     c = c > kEmit ? kEmit : c;
-    lptr[i] = cand + (static_cast<size_t>(l < num_lists ? l : 0) * kNQ + q) * kCap;
+    lptr[i] = cand + (cta * kNQ + ql) * kCap;
 #pragma unroll
     for (int ch = 0; ch < kSelChunks; ++ch) {
       const int pos = lane + 32 * ch;
@@ -388,8 +391,8 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
 constexpr int kBigStage = 2048;
 
 __global__ void __launch_bounds__(kSelThreads, 1)
-select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int cap,
-                       int k, int64_t id_base, int64_t id_stride, float* __restrict__ out_scores,
+select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ part_cnt, int num_lists, int nblk,
+                       int cap, int k, int64_t id_base, int64_t id_stride, float* __restrict__ out_scores,
                        int64_t* __restrict__ out_ids) {
   __shared__ int s_misc[4];       // [0] scratch count, [2] survivor slots
   __shared__ uint32_t s_bits[2];
@@ -402,7 +405,7 @@ select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict_
   if (threadIdx.x < 4) s_misc[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_bits[0] = 0xFFFFFFFFu; s_bits[1] = 0u; }
   if (threadIdx.x < kSelMaxLists) {
-    int c = threadIdx.x < num_lists ? part_cnt[threadIdx.x * kNQ + q] : 0;
+    int c = threadIdx.x < num_lists ? part_cnt[(static_cast<size_t>(threadIdx.x) * nblk + q / kNQ) * kNQ + q % kNQ] : 0;
     s_len[threadIdx.x] = c > cap ? cap : c;
   }
   __syncthreads();
@@ -410,7 +413,7 @@ select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict_
   // one pass over every candidate of this query: warp w takes lists w, w+32, ...; f(hi, lo) per entry
   auto for_each = [&](auto&& f) {
     for (int l = warp; l < num_lists; l += kSelWarps) {
-      const uint64_t* lst = cand + (static_cast<size_t>(l) * kNQ + q) * cap;
+      const uint64_t* lst = cand + ((static_cast<size_t>(l) * nblk + q / kNQ) * kNQ + q % kNQ) * cap;
       const int c = s_len[l];
       for (int i = lane; i < c; i += 32) f(lst[i]);
     }
@@ -496,15 +499,15 @@ select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict_
   }
 }
 
-cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int cap, int batch, int k,
+cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lists, int nblk, int cap, int batch, int k,
                           int64_t id_base, int64_t id_stride, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (batch == 0) return cudaSuccess;
   if (num_lists > kSelMaxLists) return cudaErrorInvalidValue;
   if (cap == kCap && k <= kSmallK)
-    select_topk_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, k, id_base, id_stride, out_scores,
+    select_topk_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, nblk, k, id_base, id_stride, out_scores,
                                                       out_ids);
   else
-    select_topk_big_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, cap, k, id_base, id_stride,
+    select_topk_big_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, nblk, cap, k, id_base, id_stride,
                                                           out_scores, out_ids);
   return cudaGetLastError();
 }

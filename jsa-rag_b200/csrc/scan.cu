@@ -239,8 +239,15 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
+  // Large batches: nblk query blocks (128 queries each) are scanned in the same launch.  CTA c works on
+  // block c % nblk and walks the tile sequence c / nblk, c / nblk + grid / nblk, ... — the nblk CTAs that
+  // share a tile read it at about the same time, so HBM delivers it once and the others hit the L2.
+  const int qblk = blockIdx.x % p.nblk;
+  const int first_tile = blockIdx.x / p.nblk;
+  const int tile_step = gridDim.x / p.nblk;
+  const int q_row0 = p.q_row0 + qblk * kNQ;
+  const int blk_batch = p.batch - qblk * kNQ < kNQ ? p.batch - qblk * kNQ : kNQ;   // may be <= 0: idle block
+  const uint64_t stream_hint = p.nblk > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
   // optional per-CTA cycle counters (diagnostics; zeroed by the host)
   const bool want_stats = p.stats != nullptr;
   unsigned long long* my_stats = want_stats ? p.stats + static_cast<size_t>(blockIdx.x) * kNumStats : nullptr;
@@ -256,7 +263,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     if (nk_ss > 0 && ptx::elect_one()) {  // K tail of the queries: resident in shared memory
       ptx::mbar_arrive_expect_tx(bar_qfull, nk_ss * kQChunkBytes);
       for (int kc = 0; kc < nk_ss; ++kc)
-        ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, (nk_ts + kc) * kKChunk, p.q_row0,
+        ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, (nk_ts + kc) * kKChunk, q_row0,
                          ptx::kEvictLast);
     }
     __syncwarp();
@@ -275,7 +282,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
             // tensor-map coordinates are (inner, outer): (dim, passage) for [n, dim], (passage, dim) for [dim, n]
             const int c_dim = (kc0 + c) * kKChunk, c_row = t * kTileN;
             ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * stage_bytes + c * kChunkBytes,
-                             p.b_mn ? c_row : c_dim, p.b_mn ? c_dim : c_row, ptx::kEvictFirst);
+                             p.b_mn ? c_row : c_dim, p.b_mn ? c_dim : c_row, stream_hint);
           }
         }
         __syncwarp();
@@ -349,7 +356,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     const int per_warp = p.m64 ? 16 : 32;   // queries owned by this warp
     const bool lane_ok = lane < per_warp;
     const int ql = quarter * per_warp + (lane_ok ? lane : 0);   // my query within the pass
-    const bool live = lane_ok && ql < p.batch;
+    const bool live = lane_ok && ql < blk_batch;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int cap = p.cap;
     uint64_t* warp_lists = p.cand + (static_cast<size_t>(blockIdx.x) * kNQ + quarter * per_warp) * cap;
@@ -359,7 +366,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     // ---- queries -> TMEM (A operand, K-major: column c of a chunk holds elements 2c, 2c+1) ----
     {
       const uint32_t* qrow = reinterpret_cast<const uint32_t*>(
-          static_cast<const uint16_t*>(p.qbuf) + static_cast<size_t>(p.q_row0 + ql) * p.dim);
+          static_cast<const uint16_t*>(p.qbuf) + static_cast<size_t>(q_row0 + ql) * p.dim);
       // software-pipelined: the global loads of chunk kc+1 are in flight while chunk kc is stored
       uint4 nxt[8];
       {
@@ -388,7 +395,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     // ---- per-query state lives in registers ----
     // initial threshold: the k-th best score of the sampled pre-pass when there is one (a valid
     // lower bound of the final k-th score), else -inf; dead (padding) queries never pass
-    const float seed = p.seed ? p.seed[static_cast<size_t>(ql) * p.k + (p.k - 1)] : -INFINITY;
+    const float seed = (p.seed && live) ? p.seed[static_cast<size_t>(qblk * kNQ + ql) * p.k + (p.k - 1)] : -INFINITY;
     float thr = live ? seed : INFINITY;
     uint64_t thrkey = live ? (static_cast<uint64_t>(f32_to_ord(seed)) << 32) : ~0ull;
     int cnt = 0;

@@ -378,3 +378,20 @@ def test_cuda_graph_replay_of_a_search(eng, dev):
     s2, i2 = run(q2)
     torch.cuda.synchronize()
     assert torch.equal(i2, torch.roll(i0, 1, 0))
+
+
+@pytest.mark.parametrize("n,b,k", [(150_000, 300, 100), (150_000, 512, 20), (64, 260, 10), (1_000_000, 1024, 100), (40_000, 129, 500)])
+def test_multi_block_launches_match_single_block(eng, dev, n, b, k):
+    """Batches > 128 scan 2 or 4 query blocks per launch (CTAs share each passage tile through the L2);
+    results must be bit-identical to one block per launch (debug flag 32) and agree with the oracle."""
+    e, q = _synth(n, 768, b, 5 + b, dev)
+    m = _engine(eng, e)
+    s, i = m.search(q, k)
+    m.debug_config(32, False)
+    s1, i1 = m.search(q, k)
+    m.debug_config(0, False)
+    assert torch.equal(i, i1) and torch.equal(s, s1)
+    rs, ri = _torch_ref(e, q, k)
+    exact = (q.half().double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]

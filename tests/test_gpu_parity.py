@@ -395,3 +395,40 @@ def test_multi_block_launches_match_single_block(eng, dev, n, b, k):
     exact = (q.half().double() @ e.double().T).cpu().numpy()
     rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
     assert rep["ok"], rep["errors"][:3]
+
+
+@pytest.mark.parametrize("n,b,k", [(200_000, 64, 100), (200_000, 100, 17), (1_200_000, 20, 600), (300_000, 130, 128)])
+def test_in_stream_compaction_paths(eng, dev, n, b, k):
+    """Without the sampled pre-passes (debug flag 4) every list overflows repeatedly, so the in-stream and
+    final compactions (register-resident for k <= 128, streaming for larger k) carry the search."""
+    e, q = _synth(n, 768, b, 99 + k, dev)
+    m = _engine(eng, e)
+    s0, i0 = m.search(q, k)
+    m.debug_config(4, False)
+    s1, i1 = m.search(q, k)
+    m.debug_config(0, False)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1), "seeded and unseeded searches disagree"
+    rs, ri = _torch_ref(e, q, k)
+    exact = (q.half().double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i1.cpu().numpy(), s1.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]
+
+
+@pytest.mark.parametrize("k", [100, 700])
+def test_adversarial_row_order(eng, dev, k):
+    """Scores that grow with the row number defeat the seeded thresholds (the sample is the worst part
+    of the index): correctness must then come from the running thresholds and compactions alone."""
+    n, b = 400_000, 40
+    g = torch.Generator(device=dev).manual_seed(3)
+    u = torch.nn.functional.normalize(torch.randn(b, 768, generator=g, device=dev), dim=1)
+    base = torch.nn.functional.normalize(torch.randn(n, 768, generator=g, device=dev), dim=1)
+    ramp = torch.linspace(0.0, 1.0, n, device=dev)[:, None]
+    e = (0.3 * base + ramp * u.mean(0, keepdim=True)).half()          # later rows score higher for every query
+    q = u + u.mean(0, keepdim=True)
+    m = _engine(eng, e)
+    s, i = m.search(q, k)
+    rs, ri = _torch_ref(e, q, k)
+    exact = (q.half().double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]
+    assert int(i.min()) > n // 4          # the winners sit in the late, high-scoring part of the index

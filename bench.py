@@ -257,12 +257,28 @@ def run_b200(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        scan_avg_ms = sum(scan_ms) / max(1, len(scan_ms))
-        algo_bytes = n_loc * args.dim * 2
-        achieved = algo_bytes / (scan_avg_ms * 1e-3) / 1e9 if scan_ms else None
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        n_launch = max(1, len(scan_ms))
+        scan_avg_ms = sum(scan_ms) / n_launch
+        launches_per_step = max(1, len(scan_ms) // max(1, args.steps))
+        if args.batch >= 256:
+            # several query blocks per launch: the scan is tensor-core bound (BASELINE.md crossover B* ~ 215)
+            bound, unit = "tensor", "TFLOP/s"
+            algo = 2.0 * args.batch * n_loc * args.dim / launches_per_step            # flops per launch (average)
+            achieved = algo / (scan_avg_ms * 1e-3) / 1e12 if scan_ms else None
+            if "bf16_tflops_sustained" in peaks:
+                peak, peak_src = float(peaks["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+            else:
+                peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+            algo_key = "algorithmic_flops_per_launch"
+        else:
+            bound, unit = "hbm", "GB/s"
+            algo = float(n_loc * args.dim * 2)                                         # index bytes, read once per launch
+            achieved = algo / (scan_avg_ms * 1e-3) / 1e9 if scan_ms else None
+            algo_key = "algorithmic_bytes_per_launch"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.batch == 64 and args.rows == 33_000_000:
             traffic = json.load(open(tpath)).get(f"n{world}")
         line = {
             "metric": METRIC, "value": args.batch * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -276,11 +292,11 @@ def run_b200(args):
                     "d2h_bytes_per_step": int((res_s.numel() * 4 + res_i.numel() * 8) * world)},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": "mips::mips_scan_kernel (full-shard pass)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_avg_ms,
-                         "launches_timed": len(scan_ms)},
+                         algo_key: algo, "avg_launch_ms": scan_avg_ms, "launches_timed": len(scan_ms),
+                         "launches_per_step": launches_per_step},
         }
         if world == 1 and not args.no_cpu_baseline:
             del index._store

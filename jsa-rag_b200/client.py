@@ -1,20 +1,41 @@
-"""Client of the index server — mirrors reference src/post.py (``call_retrieve_api``)."""
+"""HTTP client of the index server.
+
+``call_retrieve_api(query_embs, topk)`` keeps the calling convention of the reference's client
+(src/post.py:6-31): it returns ``(docs, scores)`` when the server answers 200 and, like the
+reference, reports the status code on stdout and returns ``None`` otherwise.  The server address is
+configurable here (the reference hard-codes its cluster host, src/post.py:21).
+"""
+from typing import Optional, Tuple
+
 import requests
 import torch
 
-DEFAULT_URL = "http://127.0.0.1:29501/retrieve"   # the reference hard-codes its cluster host (src/post.py:21)
+DEFAULT_URL = "http://127.0.0.1:29501/retrieve"
+
+
+def encode_request(query_embs: torch.Tensor, topk: int) -> dict:
+    """JSON body of POST /retrieve: the fp32 embeddings flattened row-major, their count and k
+    (RetrieveRequest, build_server/server_start.py:18-21)."""
+    flat = query_embs.detach().to(device="cpu", dtype=torch.float32).reshape(-1)
+    return {"query_embs": flat.tolist(), "bsz": int(query_embs.shape[0]), "topk": int(topk)}
+
+
+class RetrieveClient:
+    """Keeps one HTTP session (connection reuse) to an index server."""
+
+    def __init__(self, url: str = DEFAULT_URL, session=None):
+        self.url = url
+        self.session = session if session is not None else requests.Session()
+
+    def retrieve(self, query_embs: torch.Tensor, topk: int = 10) -> Optional[Tuple[list, list]]:
+        reply = self.session.post(self.url, json=encode_request(query_embs, topk))
+        if reply.status_code != 200:
+            print(f"请求失败，状态码: {reply.status_code}")   # same message as the reference client
+            return None
+        docs, scores = reply.json()[:2]
+        return docs, scores
 
 
 def call_retrieve_api(query_embs=None, topk=10, url: str = DEFAULT_URL, session=None):
-    """POSTs the flattened fp32 query embeddings; returns (docs, scores) on HTTP 200, prints and
-    returns None otherwise — exactly like src/post.py:6-31."""
-    bsz = query_embs.size(0)
-    query_embs = query_embs.to(torch.float32)
-    query_emb_list = query_embs.cpu().numpy().flatten().tolist()
-    data = {"query_embs": query_emb_list, "bsz": bsz, "topk": topk}
-    response = (session or requests).post(url, json=data)
-    if response.status_code == 200:
-        results = response.json()
-        return results[0], results[1]
-    print(f"请求失败，状态码: {response.status_code}")
-    return None
+    """Drop-in for src/post.py:call_retrieve_api."""
+    return RetrieveClient(url, session=session if session is not None else requests).retrieve(query_embs, topk)

@@ -36,6 +36,19 @@ class RetrieveClient:
         return docs, scores
 
 
+    def retrieve_binary(self, query_embs: torch.Tensor, topk: int = 10, half: bool = False):
+        """POST /retrieve_bin: raw fp32 (or fp16) query bytes instead of a JSON float list."""
+        q = query_embs.detach().to(device="cpu", dtype=torch.float16 if half else torch.float32).contiguous()
+        url = self.url.rsplit("/", 1)[0] + "/retrieve_bin"
+        reply = self.session.post(url, params={"bsz": int(q.shape[0]), "topk": int(topk), "dtype": "fp16" if half else "fp32"},
+                                  data=q.numpy().tobytes(), headers={"Content-Type": "application/octet-stream"})
+        if reply.status_code != 200:
+            print(f"请求失败，状态码: {reply.status_code}")
+            return None
+        docs, scores = reply.json()[:2]
+        return docs, scores
+
+
 def call_retrieve_api(query_embs=None, topk=10, url: str = DEFAULT_URL, session=None):
     """Drop-in for src/post.py:call_retrieve_api."""
     return RetrieveClient(url, session=session if session is not None else requests).retrieve(query_embs, topk)

@@ -25,7 +25,7 @@ import torch
 from .engine import MipsEngine, merge_topk
 
 try:  # FastAPI is only needed for the HTTP shell, not for the index itself
-    from fastapi import FastAPI, HTTPException
+    from fastapi import FastAPI, HTTPException, Request, Response
     from pydantic import BaseModel
 
     class RetrieveRequest(BaseModel):   # build_server/server_start.py:18-21
@@ -178,6 +178,35 @@ def create_app(holder: IndexHolder, rebuild_fn=None, notify=None):
         query_embs = torch.tensor(request.query_embs).view(request.bsz, -1)          # :186
         relevant_docs, scores = index.search_knn(query_embs, request.topk)           # :188
         return [relevant_docs, scores]                                              # :189
+
+    # Binary fast path next to the reference's JSON one: the request body is the raw little-endian
+    # [bsz, dim] query matrix (fp32 or fp16), so a batch of 64 x 1024 floats is 256 KB of bytes instead
+    # of ~1.2 MB of decimal text that has to be parsed float by float.
+    def _queries_from_body(body: bytes, bsz: int, dtype: str) -> torch.Tensor:
+        np_dtype = {"fp32": np.float32, "fp16": np.float16}.get(dtype)
+        if np_dtype is None or bsz <= 0 or len(body) % (bsz * np.dtype(np_dtype).itemsize) != 0:
+            raise HTTPException(status_code=422, detail="body must be bsz x dim little-endian fp32/fp16 values")
+        return torch.from_numpy(np.frombuffer(body, dtype=np_dtype).reshape(bsz, -1).copy())
+
+    @app.post("/retrieve_bin")
+    async def retrieve_bin(request: Request, bsz: int = 1, topk: int = 10, dtype: str = "fp32"):
+        """Same answer as /retrieve ([docs, scores] as JSON), binary request."""
+        index = holder.get()
+        if index is None:
+            raise HTTPException(status_code=500, detail="Index is not ready")
+        relevant_docs, scores = index.search_knn(_queries_from_body(await request.body(), bsz, dtype), topk)
+        return [relevant_docs, scores]
+
+    @app.post("/search_bin")
+    async def search_bin(request: Request, bsz: int = 1, topk: int = 10, dtype: str = "fp32"):
+        """Binary both ways, for callers that hold the passage store themselves: the response body is
+        bsz*topk fp32 scores followed by bsz*topk int64 passage ids (insertion order)."""
+        index = holder.get()
+        if index is None:
+            raise HTTPException(status_code=500, detail="Index is not ready")
+        D, I = index.search(_queries_from_body(await request.body(), bsz, dtype), topk)
+        payload = D.detach().cpu().numpy().astype("<f4").tobytes() + I.detach().cpu().numpy().astype("<i8").tobytes()
+        return Response(content=payload, media_type="application/octet-stream")
 
     @app.post("/rebuild")
     def rebuild(request: rebuildRequest):

@@ -44,6 +44,30 @@ def test_http_contract_and_client(eng):
     assert r.status_code == 200 and len(r.json()[0]) == 1 and len(r.json()[0][0]) == 10
 
 
+def test_binary_endpoints(eng):
+    import numpy as np
+    from fastapi.testclient import TestClient
+
+    class _TensorStub(_StubIndex):
+        def search(self, q, topk):
+            b = q.shape[0]
+            return (torch.arange(b * topk, dtype=torch.float32).view(b, topk), torch.arange(b * topk).view(b, topk) + 7)
+
+    holder = eng.IndexHolder(_TensorStub())
+    client = TestClient(eng.create_app(holder))
+    q = torch.randn(3, 8)
+    r = client.post("/retrieve_bin", params={"bsz": 3, "topk": 4}, content=q.numpy().tobytes())
+    assert r.status_code == 200 and holder.get().calls[-1] == ((3, 8), 4) and len(r.json()[0]) == 3
+    r = client.post("/retrieve_bin", params={"bsz": 3, "topk": 4, "dtype": "fp16"}, content=q.half().numpy().tobytes())
+    assert r.status_code == 200 and holder.get().calls[-1] == ((3, 8), 4)
+    r = client.post("/search_bin", params={"bsz": 3, "topk": 4}, content=q.numpy().tobytes())
+    body = r.content
+    assert r.status_code == 200 and len(body) == 3 * 4 * 12
+    assert np.frombuffer(body[:48], dtype="<f4").tolist() == list(range(12))
+    assert np.frombuffer(body[48:], dtype="<i8").tolist() == [x + 7 for x in range(12)]
+    assert client.post("/retrieve_bin", params={"bsz": 5, "topk": 4}, content=q.numpy().tobytes()).status_code == 422
+
+
 def test_embedding_stream_roundtrip(eng, tmp_path):
     g = load_golden("flat_n300_d1024_b5_k10")
     path = str(tmp_path / "embeddings_0.pkl")

@@ -243,14 +243,16 @@ class B200Index(object):
         return ms[sl], mi[sl]
 
     def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
-        """Captures one single-rank search (prep, seeded pre-passes, fused scan, select) for a fixed batch
-        into a CUDA graph.  Returns ``run(queries) -> (scores, ids)`` that copies the queries into the
-        captured input and replays the graph (~2 us of host time per search instead of ~40 us).
-        Multi-rank capture (NCCL collectives inside the graph) hung in testing and is refused."""
+        """Captures one search for a fixed per-rank batch into a CUDA graph — on several ranks the whole
+        distributed flow (query all-gather, fused scan + select, candidate all-gather, merge; NCCL
+        collectives are captured too).  Returns ``run(queries) -> (scores, ids)`` that copies the queries
+        into the captured input and replays the graph: a few microseconds of host time per search
+        instead of ~40 us (1 rank) / ~150 us (N ranks), which matters when a search lasts ~1 ms.
+        All ranks must call this together; ``equal_batch`` is implied.  Call ``run.release()`` (or drop
+        every reference to ``run``) BEFORE ``destroy_process_group()``: tearing the NCCL communicator
+        down while a graph that captured its kernels is alive hangs."""
         if self._store is None or not self._store.is_cuda:
             raise RuntimeError("make_graphed_search needs the index on a CUDA device; there is no CPU fallback")
-        if dist_utils.get_world_size() > 1:
-            raise NotImplementedError("graph capture of the distributed search is not supported yet")
         dev = self._store.device
         prev_equal = self.equal_batch
         self.equal_batch = True
@@ -267,12 +269,19 @@ class B200Index(object):
             out_s, out_i = self.search(static_q, topk, normalize)
         self.equal_batch = prev_equal
 
+        state = {"graph": graph, "out": (out_s, out_i)}
+
         def run(queries: torch.Tensor):
             static_q.copy_(queries, non_blocking=True)
-            graph.replay()
-            return out_s, out_i
+            state["graph"].replay()
+            return state["out"]
 
-        run.graph, run.static_input, run.outputs = graph, static_q, (out_s, out_i)
+        def release():
+            state["graph"] = None
+            state["out"] = None
+            torch.cuda.synchronize(dev)
+
+        run.release = release
         return run
 
     # ------------------------------------------------------------------ passage resolution

@@ -47,6 +47,17 @@ def main():
     ids3 = torch.tensor([[int(x["id"]) for x in row] for row in d3], device=dev)
     assert torch.equal(emb, e[ids3])
 
+    # CUDA-graph replay of the whole distributed search (collectives captured) equals the single-GPU answer
+    nb = min(sizes)
+    run = index.make_graphed_search(nb, k)
+    ref_rows = torch.cat([fi[offs[r]:offs[r] + nb] for r in range(world)])[rank * nb:(rank + 1) * nb]
+    for _ in range(2):
+        gs, gi = run(my_q[:nb])
+        torch.cuda.synchronize()
+        assert torch.equal(gi, ref_rows), "graphed search differs from the single-GPU answer"
+    run.release()
+    del run, gs, gi
+
     # uneven / empty local batches still take part in the collectives
     d4, s4 = index.search_knn(my_q[:0] if rank == world - 1 else my_q, k)
     assert (d4 == [] and s4 == []) if rank == world - 1 else len(d4) == my_q.shape[0]

@@ -26,7 +26,7 @@ def timeit(iters=10):
     return t0.elapsed_time(t1) / iters
 
 
-for name, flags in [("full", 0), ("no-select", 1)]:
+for name, flags in [("full", 0)]:
     m.debug_config(flags, False)
     ms = timeit()
     print(f"{name:10s}: {ms:.3f} ms  {n*1536/ms/1e6:.0f} GB/s", flush=True)

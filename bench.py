@@ -231,6 +231,7 @@ def run_b200(args):
     res_i = torch.empty(q_mine.shape[0], args.k, dtype=torch.int64).pin_memory()
 
     graphed = None
+    engine.debug_config(0, False)   # no event records inside the captured graph
     if world > 1:
         # a ~1 ms distributed search is sensitive to ~150 us of Python/launch overhead per step: replay a CUDA
         # graph of the same public search (collectives included); fall back to the eager call if capture fails

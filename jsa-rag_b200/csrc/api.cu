@@ -44,6 +44,10 @@ struct mips_handle {
   std::string err;
 };
 
+namespace mips {
+bool g_use_pdl = []() { const char* e = getenv("JSA_MIPS_PDL"); return !(e && e[0] == '0'); }();
+}
+
 namespace {
 
 std::string g_create_err;

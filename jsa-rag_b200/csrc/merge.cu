@@ -17,6 +17,9 @@
 
 namespace mips {
 
+__device__ __forceinline__ void ptx_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ptx_griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int kMergeWarps = 8;
 constexpr int64_t kPadId = INT64_MAX;
 
@@ -233,6 +236,8 @@ select_topk_kernel(const uint64_t* __restrict__ cand, const int* __restrict__ pa
   __shared__ uint32_t s_bits[2];  // AND / OR of all candidate score words
   __shared__ uint64_t s_win[kSmallK];
   __shared__ uint64_t s_key[kSelStage2];
+  ptx_griddep_wait();                // the candidate lists come from the scan kernel just before
+  ptx_griddep_launch_dependents();
   const int q = blockIdx.x;
   // query q of the launch lives in query block q / kNQ; its lists are those of CTAs l * nblk + q / kNQ
   const int qblk = q / kNQ, ql = q % kNQ;
@@ -398,6 +403,8 @@ select_topk_big_kernel(const uint64_t* __restrict__ cand, const int* __restrict_
   __shared__ uint32_t s_bits[2];
   __shared__ int s_len[kSelMaxLists];
   __shared__ uint64_t s_key[kBigStage];
+  ptx_griddep_wait();                // the candidate lists come from the scan kernel just before
+  ptx_griddep_launch_dependents();
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -504,12 +511,10 @@ cudaError_t launch_select(const uint64_t* cand, const int* part_cnt, int num_lis
   if (batch == 0) return cudaSuccess;
   if (num_lists > kSelMaxLists) return cudaErrorInvalidValue;
   if (cap == kCap && k <= kSmallK)
-    select_topk_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, nblk, k, id_base, id_stride, out_scores,
-                                                      out_ids);
-  else
-    select_topk_big_kernel<<<batch, kSelThreads, 0, st>>>(cand, part_cnt, num_lists, nblk, cap, k, id_base, id_stride,
-                                                          out_scores, out_ids);
-  return cudaGetLastError();
+    return launch_pdl(select_topk_kernel, dim3(batch), dim3(kSelThreads), 0, st, g_use_pdl, cand, part_cnt, num_lists, nblk,
+                      k, id_base, id_stride, out_scores, out_ids);
+  return launch_pdl(select_topk_big_kernel, dim3(batch), dim3(kSelThreads), 0, st, g_use_pdl, cand, part_cnt, num_lists,
+                    nblk, cap, k, id_base, id_stride, out_scores, out_ids);
 }
 
 template <int E>

@@ -91,6 +91,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with programmatic stream serialization may start before its predecessor in the
+// stream has finished: everything before griddep_wait() overlaps the predecessor's tail, everything
+// after it sees the predecessor's memory.  griddep_launch_dependents() lets the successor start early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMA
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;

@@ -238,6 +238,11 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // Programmatic dependent launch: let the next kernel of the stream begin its own prologue now.  Up to
+  // here nothing produced by an earlier kernel was touched; the passage index and the tensor maps are
+  // static, so the TMA producer may start streaming right away.  Whoever reads upstream results
+  // (prepared queries, seed thresholds) or writes the shared workspace calls griddep_wait() first.
+  ptx::griddep_launch_dependents();
 
   // Large batches: nblk query blocks (128 queries each) are scanned in the same launch.  CTA c works on
   // block c % nblk and walks the tile sequence c / nblk, c / nblk + grid / nblk, ... — the nblk CTAs that
@@ -260,6 +265,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   // addresses and descriptors in uniform registers and the issue loops short.
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    if (nk_ss > 0) ptx::griddep_wait();   // the K tail is read from the prepared-query buffer
     if (nk_ss > 0 && ptx::elect_one()) {  // K tail of the queries: resident in shared memory
       ptx::mbar_arrive_expect_tx(bar_qfull, nk_ss * kQChunkBytes);
       for (int kc = 0; kc < nk_ss; ++kc)
@@ -364,6 +370,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     const bool no_select = (p.flags & kDbgNoSelect) != 0;
 
     // ---- queries -> TMEM (A operand, K-major: column c of a chunk holds elements 2c, 2c+1) ----
+    ptx::griddep_wait();   // prepared queries, seed thresholds and the candidate workspace belong to earlier kernels
     {
       const uint32_t* qrow = reinterpret_cast<const uint32_t*>(
           static_cast<const uint16_t*>(p.qbuf) + static_cast<size_t>(q_row0 + ql) * p.dim);
@@ -524,8 +531,7 @@ cudaError_t configure_scan(size_t smem_bytes) {
 
 cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
                         size_t smem_bytes, cudaStream_t st) {
-  mips_scan_kernel<<<grid, kScanThreads, smem_bytes, st>>>(tmap_e, tmap_q, p);
-  return cudaGetLastError();
+  return launch_pdl(mips_scan_kernel, dim3(grid), dim3(kScanThreads), smem_bytes, st, g_use_pdl, tmap_e, tmap_q, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -547,6 +553,8 @@ __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat1
 template <typename TIn>
 __global__ void prep_queries_kernel(const TIn* __restrict__ q, int64_t q_ld, int batch, int dim, int out_dtype,
                                     int normalize, void* __restrict__ out) {
+  ptx::griddep_wait();               // the query buffer may still be read by the previous search
+  ptx::griddep_launch_dependents();
   const int row = blockIdx.x;
   __shared__ float red[32];
   float scale = 1.0f;
@@ -587,19 +595,15 @@ cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int ba
   const int threads = 256;
   switch (q_dtype) {
     case 0:
-      prep_queries_kernel<__half><<<batch_pad, threads, 0, st>>>(static_cast<const __half*>(q), q_ld, batch, dim,
-                                                                 out_dtype, normalize, out);
-      break;
+      return launch_pdl(prep_queries_kernel<__half>, dim3(batch_pad), dim3(threads), 0, st, g_use_pdl,
+                        static_cast<const __half*>(q), q_ld, batch, dim, out_dtype, normalize, out);
     case 1:
-      prep_queries_kernel<__nv_bfloat16><<<batch_pad, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(q), q_ld,
-                                                                        batch, dim, out_dtype, normalize, out);
-      break;
+      return launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3(batch_pad), dim3(threads), 0, st, g_use_pdl,
+                        static_cast<const __nv_bfloat16*>(q), q_ld, batch, dim, out_dtype, normalize, out);
     default:
-      prep_queries_kernel<float><<<batch_pad, threads, 0, st>>>(static_cast<const float*>(q), q_ld, batch, dim,
-                                                                out_dtype, normalize, out);
-      break;
+      return launch_pdl(prep_queries_kernel<float>, dim3(batch_pad), dim3(threads), 0, st, g_use_pdl,
+                        static_cast<const float*>(q), q_ld, batch, dim, out_dtype, normalize, out);
   }
-  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -307,7 +307,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
 
   const int num_tiles = static_cast<int>((h->n_local + kTileN - 1) / kTileN);
   const int grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
-  ScanParams p;
+  ScanParams p = {};
   p.n_local = h->n_local;
   p.num_tiles = num_tiles;
   p.num_kchunks = h->num_kchunks;

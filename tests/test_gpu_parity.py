@@ -432,3 +432,35 @@ def test_adversarial_row_order(eng, dev, k):
     rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
     assert rep["ok"], rep["errors"][:3]
     assert int(i.min()) > n // 4          # the winners sit in the late, high-scoring part of the index
+
+
+def test_randomised_configurations(eng, dev):
+    """Seeded random mix of shapes, dtypes, layouts, id mappings and k (interactions between the small /
+    big-k modes, M=64 / M=128 / multi-block launches, the smem K tail of dim 1024 and both layouts)."""
+    import random
+    rnd = random.Random(20260718)
+    for trial in range(14):
+        d = rnd.choice([64, 256, 768, 768, 1024])
+        n = rnd.choice([1, 63, 65, 1000, 9473, 40_000, 150_000, 300_001])
+        b = rnd.choice([1, 7, 64, 65, 128, 129, 300, 520])
+        k = min(n, rnd.choice([1, 10, 100, 128, 129, 400, 1024]))
+        dtype = rnd.choice([torch.float16, torch.bfloat16])
+        layout_dn = rnd.random() < 0.3
+        base, stride = rnd.choice([(0, 1), (3, 8), (1_000_000_007, 1)])
+        e, q = _synth(n, d, b, 1000 + trial, dev, dtype)
+        m = eng.MipsEngine(d, dtype, dev)
+        if layout_dn:
+            n_pad = (n + 7) // 8 * 8
+            e_dn = torch.zeros(d, n_pad, dtype=dtype, device=dev)
+            e_dn[:, :n] = e.T
+            m.bind(e_dn[:, :n].t(), id_base=base, id_stride=stride)
+        else:
+            m.bind(e, id_base=base, id_stride=stride)
+        s, i = m.search(q, k)
+        assert bool(((i - base) % stride == 0).all()), (trial, "id mapping")
+        rows = (i - base) // stride
+        rs, ri = _torch_ref(e, q, k, dtype)
+        exact = (q.to(dtype).double() @ e.double().T).cpu().numpy()
+        rep = O.compare_topk(rows.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+        assert rep["ok"], (trial, n, d, b, k, dtype, layout_dn, rep["errors"][:2])
+        m.close()

@@ -47,6 +47,7 @@ class B200Index(object):
         self._bound_key = None
         self._any_rank_has_queries = False
         self._last_all = None
+        self._all_counts = [0]
         # global id of local row r = id_base + r * id_stride  (see _set_sharding)
         self._id_base, self._id_stride = 0, 1
         self._sharding = "round_robin"
@@ -96,13 +97,13 @@ class B200Index(object):
     def _set_sharding(self, mode: str) -> None:
         self._sharding = mode
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
+        n = 0 if self._store is None else int(self._store.shape[0])
+        counts = dist_utils.all_gather_object(n) if w > 1 else [n]     # every rank knows every shard size
+        self._all_counts = counts
         if mode == "round_robin":
             self._id_base, self._id_stride = r, w
         else:  # contiguous: rank r owns rows [offset_r, offset_r + n_r)
-            n = 0 if self._store is None else int(self._store.shape[0])
-            counts = dist_utils.all_gather_object(n)
             self._id_base, self._id_stride = int(sum(counts[:r])), 1
-            self._all_counts = counts
         self._bound_key = None
 
     def is_index_trained(self) -> bool:
@@ -214,6 +215,10 @@ class B200Index(object):
                 dev = queries.device
                 return torch.empty(0, topk, device=dev), torch.empty(0, topk, dtype=torch.int64, device=dev)
             return self._local_search(queries, topk, normalize)
+        if topk > min(self._all_counts):
+            # the reference fails inside torch.topk on the rank whose shard is too small (and leaves the
+            # others waiting in a collective); here every rank raises the same error before communicating
+            raise RuntimeError("selected index k out of range")
         sizes = [int(queries.shape[0])] * w if self.equal_batch else dist_utils.get_varsize(queries)   # src/index.py:129
         allqueries = dist_utils.varsize_all_gather(queries, sizes)                 # src/index.py:128
         offs = np.cumsum([0] + sizes)

@@ -92,6 +92,21 @@ def test_drop_in_search_knn_matches_reference_outputs(eng, dev):
     assert len(tw.search_knn(torch.from_numpy(g["queries"]).to(dev), 5)) == 3       # build_server/index.py:261
 
 
+def test_in_place_refresh_needs_no_rebind(eng, dev):
+    """The index refresh of the reference rewrites `index.embeddings[:, a:b]` in place (src/rag.py:108-121,
+    train.py:189-204); the next search must see the new values without any extra call."""
+    e, q = _synth(20000, 768, 8, 41, dev)
+    idx = eng.B200Index()
+    idx.init_embeddings([{"id": str(i)} for i in range(20000)], dim=768)
+    idx.embeddings[:, :] = e.T
+    _, i0 = idx.search(q, 10)
+    e2, _ = _synth(20000, 768, 8, 42, dev)
+    for a in range(0, 20000, 4096):
+        idx.embeddings[:, a:a + 4096] = e2[a:a + 4096].T
+    _, i1 = idx.search(q, 10)
+    assert torch.equal(i1, _torch_ref(e2, q, 10)[1]) and not torch.equal(i0, i1)
+
+
 def test_save_load_roundtrip_on_device(eng, dev, tmp_path):
     g = load_golden("flat_n300_d1024_b5_k10")
     passages = [{"id": str(i)} for i in range(300)]

@@ -99,3 +99,31 @@ def all_gather_object(obj):
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, obj)
     return out
+
+
+def all_to_all_objects(objs, device=None):
+    """objs[d] is delivered to rank d; returns [object from rank 0, ..., object from rank W-1].
+
+    NCCL: two all_to_all_single calls (sizes, then the pickled bytes) so that every rank receives only
+    what is meant for it.  Other backends (gloo on CPU): one object all-gather, then pick."""
+    if not is_dist():
+        return list(objs)
+    w, r = dist.get_world_size(), dist.get_rank()
+    if dist.get_backend() != "nccl" or device is None or torch.device(device).type != "cuda":
+        gathered = all_gather_object(list(objs))
+        return [gathered[src][r] for src in range(w)]
+    import pickle
+    blobs = [pickle.dumps(o, protocol=pickle.HIGHEST_PROTOCOL) for o in objs]
+    in_sizes = torch.tensor([len(b) for b in blobs], dtype=torch.int64, device=device)
+    out_sizes = torch.empty_like(in_sizes)
+    dist.all_to_all_single(out_sizes, in_sizes)
+    out_list = out_sizes.tolist()
+    send = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).to(device)
+    recv = torch.empty(int(sum(out_list)), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv, send, out_list, [len(b) for b in blobs])
+    raw = recv.cpu().numpy().tobytes()
+    out, at = [], 0
+    for n in out_list:
+        out.append(pickle.loads(raw[at:at + n]))
+        at += n
+    return out

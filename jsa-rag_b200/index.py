@@ -300,20 +300,27 @@ class B200Index(object):
 
     def _resolve_docs(self, my_ids: torch.Tensor) -> List[List[dict]]:
         """global ids [b,k] -> passage dicts.  Single rank: local lookup.  Multi rank: every rank knows
-        the merged winners of *all* queries (the merge is replicated), so each owner publishes the
-        dicts it owns and one object all-gather delivers them (k winners, not W*k candidates)."""
+        the merged winners of *all* queries (the merge is replicated), so each owner sends every rank
+        exactly the dicts that rank needs (an all-to-all of pickled objects: k winners per query, not the
+        W*k candidates the reference ships through 2*W gathers)."""
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
         ids_np = my_ids.cpu().numpy()
         if w == 1:
             loc = (ids_np - self._id_base) // self._id_stride
             return self._doc_table()[loc].tolist()      # one vectorised gather instead of b*k dict lookups
-        all_ids, _ = self._last_all
-        all_np = all_ids.cpu().numpy().reshape(-1)
-        owner, local = self._owner_and_local(all_np)
-        sel = owner == r
-        mine = dict(zip(all_np[sel].tolist(), self._doc_table()[local[sel]].tolist()))
+        all_ids, offs = self._last_all
+        all_np = all_ids.cpu().numpy()
+        owner, local = self._owner_and_local(all_np.reshape(-1))
+        owner, local = owner.reshape(all_np.shape), local.reshape(all_np.shape)
+        table = self._doc_table()
+        # for every destination rank d: the passages I own among the winners of d's queries
+        outgoing = []
+        for d in range(w):
+            rows = slice(int(offs[d]), int(offs[d + 1]))
+            sel = owner[rows] == r
+            outgoing.append(dict(zip(all_np[rows][sel].tolist(), table[local[rows][sel]].tolist())))
         merged = {}
-        for part in dist_utils.all_gather_object(mine):
+        for part in dist_utils.all_to_all_objects(outgoing, device=my_ids.device):
             merged.update(part)
         return [[merged[int(g)] for g in row] for row in ids_np]
 

@@ -126,6 +126,21 @@ int mips_merge_topk_strided(int device, const float* scores, const int64_t* ids,
 int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void* out, void* stream);
 
 /*
+ * Re-rank of a short candidate list per query (one launch):
+ *   s[b, j] = <queries[b, :], cand[b, j, :]>   (fp32 accumulation), j < num_cand <= mips_max_rerank_candidates()
+ *   out_scores [batch, k] fp32 / out_pos [batch, k] int64 = the k best (score desc, position asc on ties),
+ *   out_rank   [batch, num_cand] int64 (optional, may be NULL) = rank of every candidate in the sorted order,
+ *   out_emb    [batch, k, dim] (optional, may be NULL; same dtype as cand) = cand[b, out_pos[b, j], :].
+ * queries [batch, dim] with row stride q_ld elements and cand [batch, num_cand, dim] contiguous share `dtype`
+ * (MIPS_DTYPE_F16 / BF16 / F32).  k > num_cand -> MIPS_EKRANGE.
+ * Replaces: einsum("id,ijd->ij") + torch.sort + slice + torch.gather of RAG.retrieve_with_rerank
+ * (src/rag.py:228-233) and the re-selection of the 3-tuple search_knn (build_server/index.py:253-255).
+ */
+int mips_rerank(int device, const void* queries, int64_t q_ld, const void* cand, int dtype, int batch, int num_cand,
+                int dim, int k, float* out_scores, int64_t* out_pos, int64_t* out_rank, void* out_emb, void* stream);
+int mips_max_rerank_candidates(void);
+
+/*
  * End-to-end convenience for callers that hold HOST buffers (server / ctypes clients):
  * H2D copy of fp32 queries [batch, dim], mips_search_local, D2H copy of results, stream sync.
  * host_* pointers should be page-locked for full speed but need not be.

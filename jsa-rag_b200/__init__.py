@@ -13,13 +13,16 @@ from .filtering import filter_results_by_id  # noqa: F401
 
 
 def __getattr__(name):  # lazy: engine imports need the CUDA extension
-    if name in ("MipsEngine", "merge_topk"):
+    if name in ("MipsEngine", "merge_topk", "rerank_topk"):
         from . import engine
         return getattr(engine, name)
     if name in ("B200ServerIndex", "IndexHolder", "create_app", "RetrieveRequest", "rebuildRequest",
                 "append_embedding_batch", "iter_embedding_stream", "get_pkl_files_in_directory"):
         from . import server
         return getattr(server, name)
+    if name == "rerank_passages":
+        from . import rerank
+        return rerank.rerank_passages
     if name == "call_retrieve_api":
         from . import client
         return client.call_retrieve_api

@@ -33,6 +33,9 @@ SYMBOLS = {
     "mips_merge_topk_strided": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p]),
     "mips_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mips_rerank": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_void_p]),
+    "mips_max_rerank_candidates": (c_int, []),
     "mips_search_host": (c_int, [c_void_p, POINTER(c_float), c_int, c_int, c_int, POINTER(c_float), POINTER(c_int64),
                                  c_void_p]),
     "mips_last_launch_count": (c_int, [c_void_p]),

@@ -421,6 +421,25 @@ int mips_merge_topk(int device, const float* scores, const int64_t* ids, int num
                                  stream);
 }
 
+int mips_max_rerank_candidates(void) { return rerank_max_candidates(); }
+
+int mips_rerank(int device, const void* queries, int64_t q_ld, const void* cand, int dtype, int batch, int num_cand,
+                int dim, int k, float* out_scores, int64_t* out_pos, int64_t* out_rank, void* out_emb, void* stream) {
+  if (batch < 0 || num_cand <= 0 || dim <= 0 || k <= 0 || q_ld < dim || num_cand > rerank_max_candidates() ||
+      dim > 16384 || (dtype != MIPS_DTYPE_F16 && dtype != MIPS_DTYPE_BF16 && dtype != MIPS_DTYPE_F32))
+    return fail(nullptr, MIPS_EINVAL, "mips_rerank: bad arguments batch=%d num_cand=%d dim=%d k=%d dtype=%d", batch,
+                num_cand, dim, k, dtype);
+  if (k > num_cand) return fail(nullptr, MIPS_EKRANGE, "selected index k out of range (k=%d > %d candidates)", k, num_cand);
+  if (batch == 0) return MIPS_OK;
+  if (!queries || !cand || !out_scores || !out_pos) return fail(nullptr, MIPS_EINVAL, "mips_rerank: NULL pointer");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(nullptr, MIPS_ECUDA, "cudaSetDevice(%d) failed", device);
+  cudaError_t e = launch_rerank(queries, q_ld, cand, dtype, batch, num_cand, dim, k, out_scores, out_pos, out_rank, out_emb,
+                                static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(nullptr, MIPS_ECUDA, "rerank launch failed: %s", cudaGetErrorString(e));
+  return MIPS_OK;
+}
+
 int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void* out, void* stream) {
   if (!h) return MIPS_EINVAL;
   if (!h->bound) return fail(h, MIPS_ENOTBOUND, "mips_bind_index has not been called");

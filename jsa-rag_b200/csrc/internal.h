@@ -99,6 +99,10 @@ cudaError_t configure_merge();
 cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, int layout, const int64_t* rows,
                                int64_t n, void* out, cudaStream_t st);
 
+cudaError_t launch_rerank(const void* q, int64_t q_ld, const void* cand, int dtype, int batch, int num_cand, int dim,
+                          int k, float* out_scores, int64_t* out_pos, int64_t* out_rank, void* out_emb, cudaStream_t st);
+int rerank_max_candidates();
+
 // ---- order-preserving float <-> uint32 (larger float -> larger uint) ----
 __host__ __device__ inline uint32_t f32_to_ord(float f) {
 #ifdef __CUDA_ARCH__

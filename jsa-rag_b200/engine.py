@@ -204,3 +204,33 @@ def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[tor
                              _stream_ptr(scores.device))
     N.check(rc, None, "mips_merge_topk")
     return out_s, out_i
+
+
+def rerank_topk(query_emb: torch.Tensor, cand_emb: torch.Tensor, k: int, want_rank: bool = False,
+                want_emb: bool = True):
+    """Fused re-rank of [B, L, D] candidates against [B, D] queries (one launch of mips_rerank).
+
+    Returns (scores [B,k] fp32, positions [B,k] int64, ranks [B,L] int64 or None, emb [B,k,D] or None):
+    the einsum + sort + slice + gather of reference src/rag.py:228-233."""
+    lib = N.load()
+    if query_emb.dim() != 2 or cand_emb.dim() != 3 or cand_emb.shape[0] != query_emb.shape[0] or \
+            cand_emb.shape[2] != query_emb.shape[1]:
+        raise ValueError("rerank_topk expects query_emb [B, D] and cand_emb [B, L, D]")
+    if not (query_emb.is_cuda and cand_emb.is_cuda):
+        raise RuntimeError("rerank_topk needs CUDA tensors; there is no CPU fallback")
+    dt = cand_emb.dtype if cand_emb.dtype in _TORCH2MIPS else torch.float32
+    cand = cand_emb.to(dt).contiguous()
+    q = query_emb.to(dt)
+    if q.stride(1) != 1:
+        q = q.contiguous()
+    b, L, d = cand.shape
+    dev = cand.device
+    out_s = torch.empty((b, k), dtype=torch.float32, device=dev)
+    out_p = torch.empty((b, k), dtype=torch.int64, device=dev)
+    out_r = torch.empty((b, L), dtype=torch.int64, device=dev) if want_rank else None
+    out_e = torch.empty((b, k, d), dtype=dt, device=dev) if want_emb else None
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)  # noqa: E731
+    rc = lib.mips_rerank(dev.index or 0, ptr(q), q.stride(0) if b else d, ptr(cand), _TORCH2MIPS[dt], b, L, d, int(k),
+                         ptr(out_s), ptr(out_p), ptr(out_r), ptr(out_e), _stream_ptr(dev))
+    N.check(rc, None, "mips_rerank")
+    return out_s, out_p, out_r, out_e

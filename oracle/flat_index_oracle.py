@@ -159,6 +159,25 @@ def gather_result_embeddings(embeddings_dn: torch.Tensor, indices: torch.Tensor)
 
 
 # --------------------------------------------------------------------------------------------
+# src/rag.py:228-246 — tail of retrieve_with_rerank (after the encoder)
+# --------------------------------------------------------------------------------------------
+def rerank_tail(query_emb: torch.Tensor, passage_emb: torch.Tensor, topk: int):
+    """einsum("id,ijd->ij") -> sort descending -> first topk -> gather embeddings (src/rag.py:228-233) and
+    the two statistics of src/rag.py:236-240.  Pinned by tests/golden/rerank_*.npz, which hold outputs of the
+    unmodified RAG.retrieve_with_rerank (oracle/ref_import.run_reference_rerank).
+    Returns (scores [B,k], positions [B,k], emb [B,k,D], mrr, mrr_rev)."""
+    bsz = query_emb.shape[0]
+    scores = torch.einsum("id,ijd->ij", query_emb, passage_emb)
+    sorted_scores, sorted_ids = torch.sort(scores, dim=-1, descending=True)
+    top_s, top_i = sorted_scores[:, :topk], sorted_ids[:, :topk]
+    emb = torch.gather(passage_emb, 1, top_i.unsqueeze(2).expand(bsz, topk, passage_emb.size(-1)))
+    mrr = 1 / (top_i.float() + 1).mean(-1).mean().item()
+    _, rev = torch.sort(sorted_ids, dim=-1)
+    mrr_rev = 1 / (rev[:, :topk].float() + 1).mean(-1).mean().item()
+    return top_s, top_i, emb, mrr, mrr_rev
+
+
+# --------------------------------------------------------------------------------------------
 # build_server/server_start.py:139-163 — faiss server search (normalise queries, exact IP)
 # --------------------------------------------------------------------------------------------
 def normalize_l2(x: np.ndarray) -> np.ndarray:

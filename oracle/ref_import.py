@@ -69,3 +69,90 @@ def make_reference_cpu_index(passages, embeddings_nd, dim=None):
     idx.init_embeddings(passages, dim=dim if dim is not None else embeddings_nd.shape[1])
     idx.embeddings[:, :] = embeddings_nd.T
     return idx
+
+
+def import_reference_rag():
+    """Returns the reference's ``src.rag`` module (for RAG.retrieve_with_rerank, src/rag.py:176-246).
+
+    On top of the two stubs above it needs: ``turtle`` (src/rag.py:15 imports two unused names; no tkinter
+    here), ``UntiedDualEncoderRetriever`` on the retrievers stub (src/rag.py:23), and the grpc / http client
+    modules it only calls in server mode (src/rag.py:27-33)."""
+    import_reference_index()
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+
+    stub("turtle", pos=None, register_shape=None)
+    if not hasattr(sys.modules["src.retrievers"], "UntiedDualEncoderRetriever"):
+        sys.modules["src.retrievers"].UntiedDualEncoderRetriever = type("UntiedDualEncoderRetriever", (), {})
+    stub("rebuildgrpc")
+    stub("rebuildgrpc.async_init_build_client", run_retrieve=None, run_build=None)
+    stub("post", call_retrieve_api=None)
+    import src.rag as ref_rag  # noqa: E402
+
+    return ref_rag
+
+
+class _HostTensor:
+    """A tokenizer output whose ``.cuda()`` stays on the host (src/rag.py:2364-2365 moves every value)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def cuda(self):
+        return self
+
+
+def run_reference_rerank(query_emb, passage_emb, topk, batch_size=7):
+    """Runs the UNMODIFIED ``RAG.retrieve_with_rerank`` (src/rag.py:176-246) on the host.
+
+    The encoder is out of scope, so ``self`` is a stand-in whose retriever returns rows of ``passage_emb``
+    ([B, L, D]): passage (i, j) has text "i*L+j", ``retriever_format`` is "{text}", the tokenizer maps the
+    strings back to row numbers and the retriever looks them up.  Everything after the encoder — einsum, sort,
+    slice, gather, the MRR statistics, the output lists — is the reference's own code.
+    Returns (output_passages, output_scores, query_emb, topk_passage_embd, iter_stats)."""
+    import torch
+
+    rag = import_reference_rag()
+    bsz, n_cand, dim = passage_emb.shape
+    table = passage_emb.reshape(bsz * n_cand, dim)
+    passages = [[{"id": i * n_cand + j, "title": "t", "text": str(i * n_cand + j)} for j in range(n_cand)]
+                for i in range(bsz)]
+
+    class Opt:
+        n_to_rerank_with_retrieve_with_rerank = n_cand
+        retriever_format = "{text}"
+        per_gpu_embedder_batch_size = batch_size
+        text_maxlength = 512
+
+    class Retriever:
+        def eval(self):
+            return self
+
+        def __call__(self, idx=None, is_passages=False):
+            assert is_passages
+            return table[idx.t]
+
+    class Self:
+        opt = Opt()
+
+        def _retrieve(self, index, topk_, query, ids, mask, batch_metadata, filtering_fun, iter_stats, posterior):
+            assert topk_ == n_cand
+            return passages, None, query_emb, None
+
+        def _get_fp16_retriever_copy(self, posterior=False):
+            return Retriever()
+
+        def retriever_tokenizer(self, batch, **kw):
+            return {"idx": _HostTensor(torch.tensor([int(s) for s in batch], dtype=torch.int64))}
+
+    stats = {}
+    fn = rag.RAG.retrieve_with_rerank
+    fn = getattr(fn, "__wrapped__", fn)          # peel torch.no_grad
+    with torch.no_grad():
+        out_p, out_s, q, emb = fn(Self(), None, topk, ["q"] * bsz, None, None, iter_stats=stats)
+    return out_p, out_s, q, emb, stats

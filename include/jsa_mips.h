@@ -126,6 +126,29 @@ int mips_merge_topk_strided(int device, const float* scores, const int64_t* ids,
 int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void* out, void* stream);
 
 /*
+ * Peer exchange: the exchange step of the row-sharded search fused with the merge, over NVLink peer stores
+ * (one node, one process per GPU).  Replaces the 2*W gathers + concat + topk of src/index.py:135-157 and the
+ * all-gather in front of mips_merge_topk.  Collective: every rank creates an exchange with the same world size
+ * and capacity, exports its 64-byte IPC handle, gives the handles of all ranks (rank order) to mips_xchg_connect,
+ * and then calls mips_xchg_merge once per search with the same (batch, k_in, k_out):
+ *   local_block = this rank's [fp32 scores [batch,k_in] padded to score_bytes | int64 ids [batch,k_in]]
+ *   -> out_scores / out_ids [batch, k_out] = merge of all W ranks' blocks (score desc, id asc), on every rank.
+ * Two launches per call (push, wait+merge), stream-ordered, capturable in a CUDA graph.
+ * mips_xchg_connect returns MIPS_EUNSUPPORTED when the GPUs cannot map each other's memory (callers then use the
+ * all-gather + mips_merge_topk path).
+ */
+typedef struct mips_xchg mips_xchg;
+int mips_xchg_handle_bytes(void);
+int mips_xchg_create(mips_xchg** out, int device, int rank, int world, size_t block_capacity_bytes);
+int mips_xchg_export(mips_xchg* x, void* out_handle);
+int mips_xchg_connect(mips_xchg* x, const void* all_handles);
+size_t mips_xchg_capacity(mips_xchg* x);
+int mips_xchg_merge(mips_xchg* x, const void* local_block, size_t block_bytes, size_t score_bytes, int batch, int k_in,
+                    int k_out, float* out_scores, int64_t* out_ids, void* stream);
+const char* mips_xchg_last_error(mips_xchg* x);
+int mips_xchg_destroy(mips_xchg* x);
+
+/*
  * Re-rank of a short candidate list per query (one launch):
  *   s[b, j] = <queries[b, :], cand[b, j, :]>   (fp32 accumulation), j < num_cand <= mips_max_rerank_candidates()
  *   out_scores [batch, k] fp32 / out_pos [batch, k] int64 = the k best (score desc, position asc on ties),

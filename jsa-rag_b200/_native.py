@@ -36,6 +36,14 @@ SYMBOLS = {
     "mips_rerank": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p]),
     "mips_max_rerank_candidates": (c_int, []),
+    "mips_xchg_handle_bytes": (c_int, []),
+    "mips_xchg_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_size_t]),
+    "mips_xchg_export": (c_int, [c_void_p, c_void_p]),
+    "mips_xchg_connect": (c_int, [c_void_p, c_void_p]),
+    "mips_xchg_capacity": (c_size_t, [c_void_p]),
+    "mips_xchg_merge": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mips_xchg_last_error": (c_char_p, [c_void_p]),
+    "mips_xchg_destroy": (c_int, [c_void_p]),
     "mips_search_host": (c_int, [c_void_p, POINTER(c_float), c_int, c_int, c_int, POINTER(c_float), POINTER(c_int64),
                                  c_void_p]),
     "mips_last_launch_count": (c_int, [c_void_p]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libjsa_mips.so")
-SOURCES = ["scan.cu", "merge.cu", "rerank.cu", "api.cu"]
+SOURCES = ["scan.cu", "merge.cu", "rerank.cu", "exchange.cu", "api.cu"]
 HEADERS = ["internal.h", "ptx.cuh", os.path.join("..", "..", "include", "jsa_mips.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-lcudart"]

@@ -99,6 +99,22 @@ cudaError_t configure_merge();
 cudaError_t launch_gather_rows(const void* emb, int64_t ld, int dim, int64_t n_local, int layout, const int64_t* rows,
                                int64_t n, void* out, cudaStream_t st);
 
+// ---- peer exchange (exchange.cu / merge.cu): candidate blocks pushed into every peer's slot over NVLink ----
+constexpr int kXchgMaxWorld = 16;
+constexpr size_t kXchgCtrlBytes = 512;
+struct XchgCtrl {                       // at the start of every rank's exchange buffer
+  unsigned long long epoch;             // number of pushes this rank has completed
+  unsigned int ticket;                  // CTA arrival counter of the running push
+  unsigned int pad;
+  unsigned long long flags[2][kXchgMaxWorld];   // flags[slot][src] = epoch of the last block src stored into `slot`
+};
+static_assert(sizeof(XchgCtrl) <= kXchgCtrlBytes, "control block too large");
+struct XchgPeers { uint8_t* base[kXchgMaxWorld]; };
+cudaError_t launch_xchg_push(const XchgPeers& peers, int rank, int world, const void* local_block, size_t block_bytes,
+                             size_t cap, cudaStream_t st);
+cudaError_t launch_xchg_merge(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int batch, int k_in, int k_out,
+                              float* out_scores, int64_t* out_ids, cudaStream_t st);
+
 cudaError_t launch_rerank(const void* q, int64_t q_ld, const void* cand, int dtype, int batch, int num_cand, int dim,
                           int k, float* out_scores, int64_t* out_pos, int64_t* out_rank, void* out_emb, cudaStream_t st);
 int rerank_max_candidates();

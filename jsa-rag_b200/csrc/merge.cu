@@ -84,10 +84,9 @@ __device__ __forceinline__ Cand load_cand(const float* s, const int64_t* ids, in
 }
 
 template <int kMergeE>
-__global__ void __launch_bounds__(kMergeWarps * 32)
-merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int num_lists,
-                  int64_t list_stride, int64_t id_list_stride, int k_in, int k_out, float* __restrict__ out_scores,
-                  int64_t* __restrict__ out_ids) {
+__device__ __forceinline__ void merge_lists(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,
+                                            int64_t id_list_stride, int k_in, int k_out, float* __restrict__ out_scores,
+                                            int64_t* __restrict__ out_ids) {
   constexpr int kMergeKP = 32 * kMergeE;
   extern __shared__ __align__(16) uint8_t merge_smem[];
   int64_t (*sh_id)[kMergeKP] = reinterpret_cast<int64_t (*)[kMergeKP]>(merge_smem);
@@ -144,6 +143,41 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
       out_ids[static_cast<int64_t>(q) * k_out + pos] = ok ? acc[e].id : -1;
     }
   }
+}
+
+template <int kMergeE>
+__global__ void __launch_bounds__(kMergeWarps * 32)
+merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int num_lists,
+                  int64_t list_stride, int64_t id_list_stride, int k_in, int k_out, float* __restrict__ out_scores,
+                  int64_t* __restrict__ out_ids) {
+  merge_lists<kMergeE>(scores, ids, num_lists, list_stride, id_list_stride, k_in, k_out, out_scores, out_ids);
+}
+
+// Fused exchange + merge, receiving half: the W candidate blocks of this step were (or are being) stored into
+// this GPU's exchange slot by the peers' xchg_push_kernel over NVLink.  Every CTA waits until all W arrival flags
+// carry this step's epoch, then merges straight out of the slot.  The wait is bounded: a peer that never pushes
+// traps this kernel (an error the host sees) instead of hanging the GPU.
+template <int kMergeE>
+__global__ void __launch_bounds__(kMergeWarps * 32)
+xchg_merge_kernel(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int k_in, int k_out,
+                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  XchgCtrl* ctrl = reinterpret_cast<XchgCtrl*>(local_base);
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ctrl->epoch);   // set by our own push
+  const int slot = static_cast<int>((epoch - 1) & 1);
+  if (threadIdx.x < world) {
+    const unsigned long long* flag = &ctrl->flags[slot][threadIdx.x];
+    unsigned long long seen = 0;
+    for (unsigned spins = 0;; ++spins) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (seen >= epoch) break;
+      if (spins > (1u << 26)) __trap();
+      __nanosleep(spins < 64 ? 20 : 200);
+    }
+  }
+  __syncthreads();
+  const uint8_t* slot_base = local_base + kXchgCtrlBytes + static_cast<size_t>(slot) * world * cap;
+  merge_lists<kMergeE>(reinterpret_cast<const float*>(slot_base), reinterpret_cast<const int64_t*>(slot_base + s_bytes), world,
+                       static_cast<int64_t>(cap / 4), static_cast<int64_t>(cap / 8), k_in, k_out, out_scores, out_ids);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -528,8 +562,28 @@ static cudaError_t launch_merge_e(const float* scores, const int64_t* ids, int n
 }
 
 cudaError_t configure_merge() {
-  return cudaFuncSetAttribute(merge_topk_kernel<kMaxK / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              kMergeWarps * kMaxK * static_cast<int>(sizeof(int64_t) + sizeof(uint32_t)));
+  const int smem = kMergeWarps * kMaxK * static_cast<int>(sizeof(int64_t) + sizeof(uint32_t));
+  cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel<kMaxK / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(xchg_merge_kernel<kMaxK / 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+cudaError_t launch_xchg_merge(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int batch, int k_in, int k_out,
+                              float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  if (batch == 0) return cudaSuccess;
+  const int kk = k_in > k_out ? k_in : k_out;
+  if (kk <= kSmallK) {
+    constexpr int E = kSmallK / 32;
+    const size_t smem = static_cast<size_t>(kMergeWarps) * 32 * E * (sizeof(int64_t) + sizeof(uint32_t));
+    xchg_merge_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(local_base, world, cap, s_bytes, k_in, k_out, out_scores, out_ids);
+    return cudaGetLastError();
+  }
+  static cudaError_t cfg = configure_merge();
+  if (cfg != cudaSuccess) return cfg;
+  constexpr int E = kMaxK / 32;
+  const size_t smem = static_cast<size_t>(kMergeWarps) * 32 * E * (sizeof(int64_t) + sizeof(uint32_t));
+  xchg_merge_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(local_base, world, cap, s_bytes, k_in, k_out, out_scores, out_ids);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,

@@ -236,9 +236,14 @@ class B200Index(object):
             if topk > n_local:
                 raise RuntimeError("selected index k out of range")
             self._get_engine().search(allqueries, topk, normalize=normalize, out=(ls[0], li[0]))   # src/index.py:132
-            gathered = torch.empty((w, buf.shape[1]), dtype=torch.uint8, device=buf.device)
-            torch.distributed.all_gather_into_tensor(gathered, buf[0])                             # replaces :139-142
-            ms, mi = merge_packed(gathered, bt, topk, topk)                                          # replaces :143-157
+            xchg = self._peer_exchange(int(buf.shape[1]), buf.device)
+            if xchg is not None:
+                # NVLink peer stores into every rank's slot + wait-and-merge kernel (replaces :135-157)
+                ms, mi = xchg.merge(buf[0], bt, topk, topk)
+            else:
+                gathered = torch.empty((w, buf.shape[1]), dtype=torch.uint8, device=buf.device)
+                torch.distributed.all_gather_into_tensor(gathered, buf[0])                         # replaces :139-142
+                ms, mi = merge_packed(gathered, bt, topk, topk)                                      # replaces :143-157
         else:
             ls, li = self._local_search(allqueries, topk, normalize)               # src/index.py:132
             gs, gi = dist_utils.all_gather_candidates(ls, li)                      # replaces :139-142
@@ -246,6 +251,30 @@ class B200Index(object):
         sl = slice(int(offs[r]), int(offs[r + 1]))
         self._last_all = (mi, offs)
         return ms[sl], mi[sl]
+
+    def _peer_exchange(self, block_bytes: int, device):
+        """The exchange object for blocks of ``block_bytes`` (created or grown collectively: block sizes derive
+        from the global batch and k, which are the same on every rank)."""
+        x = getattr(self, "_xchg", None)
+        if x is False:
+            return None
+        if x is not None and x.capacity >= block_bytes:
+            return x
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the peer exchange must be sized before graph capture (run one eager search first)")
+        from .exchange import make_peer_exchange
+        if x is not None:
+            x.close()
+        x = make_peer_exchange(device, max(block_bytes, getattr(self, "_xchg_min_bytes", 1 << 20)))
+        self._xchg = x if x is not None else False
+        return x
+
+    def close_exchange(self):
+        """Collective.  Releases the peer-mapped exchange buffer (call before destroy_process_group())."""
+        x = getattr(self, "_xchg", None)
+        if x:
+            x.close()
+        self._xchg = None
 
     def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
         """Captures one search for a fixed per-rank batch into a CUDA graph — on several ranks the whole

@@ -34,9 +34,34 @@ def main():
     index = eng.B200Index()
     index.init_embeddings(passages, dim=d)
     index.embeddings[:, :] = e[rank::world].T
+    index._xchg_min_bytes = 1024            # start with a tight exchange so that the k = 1000 search below has to grow it
     s, i = index.search(my_q, k)
     assert torch.equal(i, fi[offs[rank]:offs[rank + 1]]), "distributed ids differ from the single-GPU answer"
     assert torch.equal(s, fs[offs[rank]:offs[rank + 1]]), "distributed scores differ from the single-GPU answer"
+
+    # the exchange step ran as NVLink peer stores + wait-and-merge (mips_xchg_merge); the NCCL all-gather +
+    # mips_merge_topk path must give the same bits
+    p2p = bool(getattr(index, "_xchg", None))
+    if os.environ.get("JSA_MIPS_EXCHANGE", "p2p") == "p2p" and os.environ.get("JSA_REQUIRE_P2P", "1") == "1":
+        assert p2p, "peer exchange was not set up on this box"
+    saved, index._xchg = index._xchg, False
+    s_n, i_n = index.search(my_q, k)
+    index._xchg = saved
+    assert torch.equal(i_n, i) and torch.equal(s_n, s)
+    # back-to-back searches without host syncs: slots alternate, a fast rank may run ahead by one step
+    outs = []
+    for t in range(40):
+        outs.append(index.search(my_q.roll(t, 0), k)[1])
+    for t, o in enumerate(outs):
+        assert torch.equal(o, fi[offs[rank]:offs[rank + 1]].roll(t, 0)), f"step {t} differs"
+    # growing the exchange (bigger blocks: k = 1000) is collective and transparent
+    cap0 = index._xchg.capacity if p2p else 0
+    fs2, fi2 = full.search(q_all, 1000)
+    s2, i2 = index.search(my_q, 1000)
+    assert torch.equal(i2, fi2[offs[rank]:offs[rank + 1]]) and torch.equal(s2, fs2[offs[rank]:offs[rank + 1]])
+    assert not p2p or index._xchg.capacity > cap0
+    s2, i2 = index.search(my_q, k)
+    assert torch.equal(i2, i)
 
     docs, scores = index.search_knn(my_q, k)
     ids = torch.tensor([[int(x["id"]) for x in row] for row in docs])
@@ -61,9 +86,10 @@ def main():
     # uneven / empty local batches still take part in the collectives
     d4, s4 = index.search_knn(my_q[:0] if rank == world - 1 else my_q, k)
     assert (d4 == [] and s4 == []) if rank == world - 1 else len(d4) == my_q.shape[0]
+    index.close_exchange()
     dist.barrier()
     if rank == 0:
-        print(f"nccl worker ok: world={world}")
+        print(f"nccl worker ok: world={world} exchange={'p2p' if p2p else 'nccl'}")
     dist.destroy_process_group()
 
 

@@ -219,7 +219,10 @@ def run_b200(args):
     t_wall1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     scan_ms = engine.scan_times_ms()
-    launches = engine.last_launch_count() + (1 if world > 1 else 0)
+    p2p = bool(getattr(index, "_xchg", None))
+    # own kernels per step: the local search + (push, wait+merge) with the peer exchange, or the merge after NCCL
+    p2p_q = bool(getattr(index, "_xchg_q", None))
+    launches = engine.last_launch_count() + (((2 if p2p else 1) + (2 if p2p_q else 0)) if world > 1 else 0)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,7 +307,8 @@ def run_b200(args):
             "metric": METRIC, "value": args.batch * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
-            "config": workload(args, world),
+            "config": dict(workload(args, world), **({"exchange": "nvlink peer stores (queries and candidates) + wait-and-merge kernel" if p2p
+                                                      else "nccl all-gather + merge kernel"} if world > 1 else {})),
             "e2e": {"value": args.batch * args.steps / e2e_s, "unit": UNIT,
                     "path": "mips_search_host (C ABI, host buffers)" if world == 1 else
                             ("B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)"
@@ -334,6 +338,7 @@ def run_b200(args):
         if graphed is not None:
             graphed.release()          # graphs that captured NCCL kernels must die before the communicator
         torch.cuda.synchronize()
+        index.close_exchange()         # collective: peer-mapped exchange buffers are unmapped before anyone frees
         dist.barrier()
         dist.destroy_process_group()
         guard.cancel()

@@ -145,6 +145,9 @@ int mips_xchg_connect(mips_xchg* x, const void* all_handles);
 size_t mips_xchg_capacity(mips_xchg* x);
 int mips_xchg_merge(mips_xchg* x, const void* local_block, size_t block_bytes, size_t score_bytes, int batch, int k_in,
                     int k_out, float* out_scores, int64_t* out_ids, void* stream);
+/* Plain all-gather over the same mechanism (the query all-gather of src/index.py:128): every rank's `block_bytes`
+ * (equal on all ranks, multiple of 8) -> out [W, block_bytes] in rank order on every rank.  Two launches. */
+int mips_xchg_gather(mips_xchg* x, const void* local_block, size_t block_bytes, void* out, void* stream);
 const char* mips_xchg_last_error(mips_xchg* x);
 int mips_xchg_destroy(mips_xchg* x);
 

@@ -42,6 +42,7 @@ SYMBOLS = {
     "mips_xchg_connect": (c_int, [c_void_p, c_void_p]),
     "mips_xchg_capacity": (c_size_t, [c_void_p]),
     "mips_xchg_merge": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mips_xchg_gather": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mips_xchg_last_error": (c_char_p, [c_void_p]),
     "mips_xchg_destroy": (c_int, [c_void_p]),
     "mips_search_host": (c_int, [c_void_p, POINTER(c_float), c_int, c_int, c_int, POINTER(c_float), POINTER(c_int64),

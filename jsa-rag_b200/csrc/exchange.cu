@@ -48,7 +48,43 @@ xchg_push_kernel(XchgPeers peers, int rank, int world, const uint2* __restrict__
     *reinterpret_cast<volatile unsigned long long*>(&ctrl->epoch) = epoch + 1;
   }
 }
+
+// Receiving half of a plain all-gather (used for the queries): waits for the W arrival flags of this epoch, then
+// copies the W blocks out of the slot into one contiguous [W, block] array, so the slot can be reused two steps later.
+__global__ void __launch_bounds__(kPushThreads)
+xchg_gather_kernel(uint8_t* local_base, int world, size_t cap, size_t n8, uint2* __restrict__ out) {
+  XchgCtrl* ctrl = reinterpret_cast<XchgCtrl*>(local_base);
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ctrl->epoch);
+  const int slot = static_cast<int>((epoch - 1) & 1);
+  if (threadIdx.x < world) {
+    const unsigned long long* flag = &ctrl->flags[slot][threadIdx.x];
+    unsigned long long seen = 0;
+    for (unsigned spins = 0;; ++spins) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (seen >= epoch) break;
+      if (spins > (1u << 26)) __trap();
+      __nanosleep(spins < 64 ? 20 : 200);
+    }
+  }
+  __syncthreads();
+  const uint8_t* slot_base = local_base + kXchgCtrlBytes + static_cast<size_t>(slot) * world * cap;
+  const size_t total = n8 * world;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kPushThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kPushThreads + threadIdx.x; i < total; i += stride) {
+    const size_t src = i / n8, off = i - src * n8;
+    out[i] = reinterpret_cast<const uint2*>(slot_base + src * cap)[off];
+  }
+}
 }  // namespace
+
+cudaError_t launch_xchg_gather(uint8_t* local_base, int world, size_t cap, size_t block_bytes, void* out, cudaStream_t st) {
+  const size_t n8 = block_bytes / 8;
+  size_t grid = (n8 * world + kPushThreads * 4 - 1) / (kPushThreads * 4);
+  if (grid < 1) grid = 1;
+  if (grid > 128) grid = 128;
+  xchg_gather_kernel<<<static_cast<unsigned>(grid), kPushThreads, 0, st>>>(local_base, world, cap, n8, static_cast<uint2*>(out));
+  return cudaGetLastError();
+}
 
 cudaError_t launch_xchg_push(const XchgPeers& peers, int rank, int world, const void* local_block, size_t block_bytes,
                              size_t cap, cudaStream_t st) {
@@ -170,6 +206,21 @@ int mips_xchg_merge(mips_xchg* x, const void* local_block, size_t block_bytes, s
   if (e != cudaSuccess) return xfail(x, MIPS_ECUDA, "push launch failed", e);
   e = launch_xchg_merge(x->local, x->world, x->cap, score_bytes, batch, k_in, k_out, out_scores, out_ids, st);
   if (e != cudaSuccess) return xfail(x, MIPS_ECUDA, "merge launch failed", e);
+  return MIPS_OK;
+}
+
+int mips_xchg_gather(mips_xchg* x, const void* local_block, size_t block_bytes, void* out, void* stream) {
+  if (!x) return MIPS_EINVAL;
+  if (!x->connected) return xfail(x, MIPS_ENOTBOUND, "mips_xchg_connect has not been called");
+  if (block_bytes % 8 || block_bytes > x->cap) return xfail(x, MIPS_EINVAL, "block must be a multiple of 8 bytes and <= capacity");
+  if (block_bytes == 0) return MIPS_OK;
+  if (!local_block || !out) return xfail(x, MIPS_EINVAL, "NULL pointer");
+  XDeviceGuard g(x->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = launch_xchg_push(x->peers, x->rank, x->world, local_block, block_bytes, x->cap, st);
+  if (e != cudaSuccess) return xfail(x, MIPS_ECUDA, "push launch failed", e);
+  e = launch_xchg_gather(x->local, x->world, x->cap, block_bytes, out, st);
+  if (e != cudaSuccess) return xfail(x, MIPS_ECUDA, "gather launch failed", e);
   return MIPS_OK;
 }
 

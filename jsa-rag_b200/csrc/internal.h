@@ -112,6 +112,7 @@ static_assert(sizeof(XchgCtrl) <= kXchgCtrlBytes, "control block too large");
 struct XchgPeers { uint8_t* base[kXchgMaxWorld]; };
 cudaError_t launch_xchg_push(const XchgPeers& peers, int rank, int world, const void* local_block, size_t block_bytes,
                              size_t cap, cudaStream_t st);
+cudaError_t launch_xchg_gather(uint8_t* local_base, int world, size_t cap, size_t block_bytes, void* out, cudaStream_t st);
 cudaError_t launch_xchg_merge(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int batch, int k_in, int k_out,
                               float* out_scores, int64_t* out_ids, cudaStream_t st);
 

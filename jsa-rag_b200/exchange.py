@@ -63,6 +63,19 @@ class PeerExchange:
             raise RuntimeError("mips_xchg_merge: " + (self._lib.mips_xchg_last_error(self._h) or b"").decode())
         return out_s, out_i
 
+    def gather(self, local: torch.Tensor) -> torch.Tensor:
+        """All-gather of equally shaped contiguous tensors: returns [W, *local.shape] (rank order)."""
+        if not self.ok:
+            raise RuntimeError("peer exchange is not connected")
+        local = local.contiguous()
+        out = torch.empty((self.world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        rc = self._lib.mips_xchg_gather(self._h, ctypes.c_void_p(local.data_ptr()), local.numel() * local.element_size(),
+                                        ctypes.c_void_p(out.data_ptr()),
+                                        ctypes.c_void_p(torch.cuda.current_stream(local.device).cuda_stream))
+        if rc != N.MIPS_OK:
+            raise RuntimeError("mips_xchg_gather: " + (self._lib.mips_xchg_last_error(self._h) or b"").decode())
+        return out
+
     def _free(self):
         if self._h:
             self._lib.mips_xchg_destroy(self._h)

@@ -204,7 +204,8 @@ class B200Index(object):
         """Tensor-native distributed search: this rank's queries -> (scores fp32 [b,k], global ids [b,k]).
 
         All ranks must call it together (like the reference's search_knn).  Steps: all-gather
-        queries -> local fused search -> one all-gather of candidates -> device merge -> own rows.
+        queries -> local fused search -> exchange of candidates -> device merge -> own rows.  On one node
+        both exchanges are NVLink peer stores (exchange.py); otherwise NCCL all-gathers.
         """
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
         self._any_rank_has_queries = False
@@ -220,7 +221,15 @@ class B200Index(object):
             # others waiting in a collective); here every rank raises the same error before communicating
             raise RuntimeError("selected index k out of range")
         sizes = [int(queries.shape[0])] * w if self.equal_batch else dist_utils.get_varsize(queries)   # src/index.py:129
-        allqueries = dist_utils.varsize_all_gather(queries, sizes)                 # src/index.py:128
+        allqueries = None
+        nbytes = queries.numel() * queries.element_size()
+        if queries.is_cuda and sizes[0] > 0 and len(set(sizes)) == 1 and nbytes % 8 == 0 and queries.dim() == 2 \
+                and torch.distributed.get_backend() == "nccl":
+            xq = self._peer_exchange(nbytes, queries.device, "_xchg_q")
+            if xq is not None:                                                     # NVLink peer stores, no collective call
+                allqueries = xq.gather(queries).view(w * sizes[0], queries.shape[1])
+        if allqueries is None:
+            allqueries = dist_utils.varsize_all_gather(queries, sizes)             # src/index.py:128
         offs = np.cumsum([0] + sizes)
         if allqueries.shape[0] == 0:
             return (torch.empty(0, topk, device=queries.device),
@@ -252,11 +261,12 @@ class B200Index(object):
         self._last_all = (mi, offs)
         return ms[sl], mi[sl]
 
-    def _peer_exchange(self, block_bytes: int, device):
-        """The exchange object for blocks of ``block_bytes`` (created or grown collectively: block sizes derive
-        from the global batch and k, which are the same on every rank)."""
-        x = getattr(self, "_xchg", None)
-        if x is False:
+    def _peer_exchange(self, block_bytes: int, device, which: str = "_xchg"):
+        """The exchange object for blocks of ``block_bytes`` — ``_xchg`` for candidates, ``_xchg_q`` for queries
+        (created or grown collectively: block sizes derive from the global batch and k, which are the same on
+        every rank).  None when the ranks cannot map each other's memory: the caller then uses NCCL."""
+        x = getattr(self, which, None)
+        if x is False or getattr(self, "_p2p_off", False):
             return None
         if x is not None and x.capacity >= block_bytes:
             return x
@@ -266,15 +276,18 @@ class B200Index(object):
         if x is not None:
             x.close()
         x = make_peer_exchange(device, max(block_bytes, getattr(self, "_xchg_min_bytes", 1 << 20)))
-        self._xchg = x if x is not None else False
+        if x is None:
+            self._p2p_off = True
+        setattr(self, which, x)
         return x
 
     def close_exchange(self):
-        """Collective.  Releases the peer-mapped exchange buffer (call before destroy_process_group())."""
-        x = getattr(self, "_xchg", None)
-        if x:
-            x.close()
-        self._xchg = None
+        """Collective.  Releases the peer-mapped exchange buffers (call before destroy_process_group())."""
+        for which in ("_xchg", "_xchg_q"):
+            x = getattr(self, which, None)
+            if x:
+                x.close()
+            setattr(self, which, None)
 
     def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
         """Captures one search for a fixed per-rank batch into a CUDA graph — on several ranks the whole

@@ -74,8 +74,13 @@ def main():
 
     # CUDA-graph replay of the whole distributed search (collectives captured) equals the single-GPU answer
     nb = min(sizes)
-    run = index.make_graphed_search(nb, k)
     ref_rows = torch.cat([fi[offs[r]:offs[r] + nb] for r in range(world)])[rank * nb:(rank + 1) * nb]
+    # equal per-rank batches: the query all-gather also runs over the peer exchange (mips_xchg_gather)
+    for t in range(6):
+        es, ei = index.search(my_q[:nb].roll(t, 0), k)
+        assert torch.equal(ei, ref_rows.roll(t, 0)), "equal-batch search differs from the single-GPU answer"
+    assert not p2p or bool(getattr(index, "_xchg_q", None)), "queries did not go through the peer exchange"
+    run = index.make_graphed_search(nb, k)
     for _ in range(2):
         gs, gi = run(my_q[:nb])
         torch.cuda.synchronize()

@@ -4,7 +4,8 @@ The reference needs 3 + 4*W small collectives per search (src/dist_utils.py:47-1
 src/index.py:128-142) and ships pickled passage text for all W*k candidates.  Here a search uses
 one size exchange + one padded query all-gather (same contract as ``varsize_all_gather``) and ONE
 all-gather of packed (score, id) candidates; passage text is resolved after the merge, for the k
-winners only.
+winners only.  On one node ``B200Index.search`` replaces both tensor all-gathers with NVLink peer
+stores (``exchange.py``); the functions here remain the multi-node / gloo path.
 """
 from __future__ import annotations
 

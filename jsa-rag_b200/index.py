@@ -29,6 +29,18 @@ from . import dist_utils
 EMBEDDINGS_DIM: int = 768  # reference src/retrievers.py:14
 
 
+_LOAD_CHUNK = 1 << 20
+
+
+def _load_shard(path: str) -> torch.Tensor:
+    """A saved [D, n_s] shard (src/index.py:80 writes it with torch.save) as a host tensor; memory-mapped when the
+    file is in the zip format, so that load_index never holds a whole shard set in host memory."""
+    try:
+        return torch.load(path, map_location="cpu", mmap=True)
+    except Exception:
+        return torch.load(path, map_location="cpu")
+
+
 class B200Index(object):
     def __init__(self, dtype: torch.dtype = torch.float16, device: Optional[str] = None, layout: str = "nd"):
         """``layout``: physical storage of the matrix.  "nd" (default) = one contiguous row per passage
@@ -153,7 +165,7 @@ class B200Index(object):
         for shard_id in range(rank * shards_per_worker, (rank + 1) * shards_per_worker):
             with open(self._get_saved_passages_path(path, shard_id), "rb") as fobj:
                 passages.append(pickle.load(fobj))
-            shards.append(torch.load(self._get_saved_embedding_path(path, shard_id), map_location="cpu"))
+            shards.append(_load_shard(self._get_saved_embedding_path(path, shard_id)))
         self.doc_map = {}
         n_passages = 0
         for chunk in passages:
@@ -165,8 +177,17 @@ class B200Index(object):
         self._store = self._alloc(n, dim)
         at = 0
         for s in shards:
-            self._store[at:at + s.shape[1]].copy_(s.t())
-            at += int(s.shape[1])
+            n_s = int(s.shape[1])
+            if self._store.is_cuda:
+                # stream: <= 1M columns at a time host -> device as stored ([D, cols]), transposed into the K-major
+                # rows on the device; host peak = one chunk (the shard itself is memory-mapped), device peak = + one chunk
+                for c0 in range(0, n_s, _LOAD_CHUNK):
+                    c1 = min(n_s, c0 + _LOAD_CHUNK)
+                    blk = s[:, c0:c1].to(self._store.device)
+                    self._store[at + c0:at + c1].copy_(blk.t())
+            else:
+                self._store[at:at + n_s].copy_(s.t())
+            at += n_s
         self._set_sharding("contiguous")
 
     # ------------------------------------------------------------------ native search

@@ -119,6 +119,16 @@ def test_save_load_roundtrip_on_device(eng, dev, tmp_path):
     d1, s1 = idx.search_knn(torch.from_numpy(g["queries"]).to(dev), 10)
     d2, s2 = idx2.search_knn(torch.from_numpy(g["queries"]).to(dev), 10)
     assert d1 == d2 and s1 == s2
+    # shards stream to the device in column chunks (here 37 columns at a time): same matrix
+    import importlib
+    mod = importlib.import_module("jsa-rag_b200.index")
+    saved, mod._LOAD_CHUNK = mod._LOAD_CHUNK, 37
+    try:
+        idx3 = eng.B200Index()
+        idx3.load_index(str(tmp_path), 3)
+    finally:
+        mod._LOAD_CHUNK = saved
+    assert torch.equal(idx3.embeddings, idx.embeddings) and idx3.doc_map == idx.doc_map
 
 
 # ------------------------------------------------------------------ oracle on seeded inputs, edge cases

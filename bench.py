@@ -189,7 +189,8 @@ def run_b200(args):
     q_host = q_mine.cpu().pin_memory()
 
     engine = index._get_engine()
-    engine.debug_config(8, False)   # flag 8: CUDA events around every full-shard scan launch
+    dbg = int(os.environ.get("JSA_MIPS_FLAGS", "0"))   # A/B switches of include/jsa_mips.h (0 = product path)
+    engine.debug_config(8 | dbg, False)   # flag 8: CUDA events around every full-shard scan launch
 
     def step():
         return index.search(q_mine, args.k)
@@ -234,7 +235,7 @@ def run_b200(args):
     res_i = torch.empty(q_mine.shape[0], args.k, dtype=torch.int64).pin_memory()
 
     graphed = None
-    engine.debug_config(0, False)   # no event records inside the captured graph
+    engine.debug_config(dbg, False)   # no event records inside the captured graph
     if world > 1:
         # a ~1 ms distributed search is sensitive to ~150 us of Python/launch overhead per step: replay a CUDA
         # graph of the same public search (collectives included); fall back to the eager call if capture fails

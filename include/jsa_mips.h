@@ -180,7 +180,8 @@ int mips_last_launch_count(const mips_handle* h);
 /*
  * Diagnostics (not used on the product path).  flags: 1 = skip the select epilogue, 2 = skip the
  * MMAs (pure TMA streaming) — results are meaningless with either set; 4 = no sampled pre-pass;
- * 8 = time the scan launches.  stats_dev: device array of
+ * 8 = time the scan launches; 16 = always UMMA M=128; 32 = one query block per launch; 64 = seed the thresholds
+ * with separate sampled scan + select launches instead of inside the scan kernel.  stats_dev: device array of
  * [mips_num_sms()][mips_debug_num_stats()] uint64 per-CTA cycle counters the scan kernel fills
  * (caller zeroes it), or NULL.  Counter order: producer wait, MMA wait(full), MMA wait(TMEM),
  * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles.

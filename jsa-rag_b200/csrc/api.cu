@@ -31,6 +31,7 @@ struct mips_handle {
   // internal buffers
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  void* sync = nullptr;  // zero-initialised: grid barrier words | seeds of the in-kernel sampled pre-pass
   void* io = nullptr;  // device staging for mips_search_host: queries | scores | ids
   size_t io_bytes = 0;
   int last_launches = 0;
@@ -135,7 +136,7 @@ int encode_2d_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t row
 }
 
 struct WsLayout {
-  size_t q_off, cand_off, pk_off, seed_s_off, seed_i_off, total;
+  size_t q_off, cand_off, pk_off, seed_s_off, seed_i_off, top_off, total;
 };
 
 WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
@@ -149,6 +150,7 @@ WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
   w.pk_off = off;   off += align_up(grid * kNQ * sizeof(int), 1024);
   w.seed_s_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * max_k * sizeof(float), 1024);
   w.seed_i_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * max_k * sizeof(int64_t), 1024);
+  w.top_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * grid * kTopJ * sizeof(uint32_t), 1024);
   w.total = off;
   return w;
 }
@@ -211,6 +213,15 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
     delete h;
     return fail(nullptr, MIPS_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", h->smem_bytes, cudaGetErrorString(e));
   }
+  constexpr size_t kSyncBytes = 256 + 4 * kNQ * sizeof(uint32_t);
+  e = cudaMalloc(&h->sync, kSyncBytes);
+  if (e == cudaSuccess) e = cudaMemset(h->sync, 0, kSyncBytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    if (h->sync) cudaFree(h->sync);
+    delete h;
+    return fail(nullptr, MIPS_ECUDA, "allocating the barrier words failed: %s", cudaGetErrorString(e));
+  }
   *out = h;
   return MIPS_OK;
 }
@@ -218,6 +229,7 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
 void mips_destroy(mips_handle* h) {
   if (!h) return;
   DeviceGuard g(h->device);
+  if (h->sync) cudaFree(h->sync);
   if (h->ws) cudaFree(h->ws);
   if (h->io) cudaFree(h->io);
   if (h->timing_ready)
@@ -377,6 +389,18 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
         if (nxt <= p.emit / kTileN) break;   // an unseeded pass this short leaves <= emit candidates per list
       }
       for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
+    }
+    // k <= 128: the last (largest) sample is scanned by the full-shard launch itself (phase A / grid barrier /
+    // phase B inside the kernel), so a search is prep + scan + select.  Needs every CTA resident (grid <= SMs, one
+    // CTA per SM), kTopJ values per list enough to cover k, and one epilogue warp per launch query for phase B.
+    p.sample_tiles = 0;
+    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) && launch_grid <= h->num_sms &&
+        nslots * kTopJ >= k && nslots * kTopJ <= 32 * kSeedE && launch_grid * 4 >= p.batch) {
+      p.sample_tiles = levels[n_levels - 1];
+      p.top = reinterpret_cast<uint32_t*>(ws + w.top_off);
+      p.gsync = static_cast<unsigned*>(h->sync);
+      p.seed_ord = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->sync) + 256);
+      n_levels = 0;
     }
     for (int lv = 0; lv < n_levels; ++lv) {
       ScanParams pp = p;

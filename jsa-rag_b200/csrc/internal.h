@@ -54,13 +54,24 @@ struct ScanParams {
   const float* seed;     // optional [kNQ][k] sorted scores of the sampled pre-pass (NULL = none)
   int flags;             // diagnostics: kDbgNoSelect / kDbgNoMma (results are then meaningless)
   unsigned long long* stats;  // optional [grid][kNumStats] per-CTA cycle counters (NULL = off)
+  // In-kernel sampled seeding (k <= kSmallK): every CTA first scans its own first `sample_tiles` tiles keeping only
+  // the kTopJ best scores per query, the grid synchronises, one warp per query takes the k-th best of all CTAs'
+  // values (a valid lower bound of the final k-th score), the grid synchronises again and the full scan starts
+  // with that threshold.  0 = off (the thresholds come from `seed` or start at -inf).
+  int sample_tiles;
+  uint32_t* top;         // [nblk * kNQ][grid / nblk][kTopJ] orderable score images
+  uint32_t* seed_ord;    // [nblk * kNQ] seeds produced by phase B
+  unsigned* gsync;       // {arrival count, generation}: self-resetting grid barrier
 };
+constexpr int kTopJ = 4;
+constexpr int kSeedE = 19;   // 32 * 19 = 608 >= 148 lists * kTopJ values handled by one warp
 
 constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
 constexpr int kDbgNoMma = 2;     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
 constexpr int kDbgNoSeed = 4;    // disable the sampled pre-passes (thresholds start at -inf)
 constexpr int kDbgForceM128 = 16; // always use UMMA M=128 (A/B test of the M=64 small-batch mode)
 constexpr int kDbgOneBlock = 32;  // one query block per launch even for large batches (A/B test of the L2-shared multi-block scan)
+constexpr int kDbgHostPrepass = 64; // seed thresholds with separate sampled scan + select launches (the pre-fusion path; always used for k > 128)
 constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };

@@ -182,6 +182,33 @@ __device__ __forceinline__ uint32_t pick64(const uint32_t (&r0)[32], const uint3
   return t[0];
 }
 
+// Grid-wide barrier for the persistent scan (grid <= number of SMs, one CTA per SM, so every CTA is
+// resident).  One thread per CTA calls it.  Self-resetting: the last arriver clears the count and
+// bumps the generation the others poll, so the same two words serve every launch and graph replay.
+// Bounded: a CTA that never arrives traps the kernel instead of hanging the GPU.
+__device__ __forceinline__ void grid_sync(unsigned* gsync, unsigned n_ctas) {
+  unsigned* count = gsync;
+  unsigned* gen = gsync + 1;
+  unsigned g;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(gen) : "memory");
+  __threadfence();
+  const unsigned prev = atomicAdd(count, 1u);
+  if (prev == n_ctas - 1) {
+    *reinterpret_cast<volatile unsigned*>(count) = 0u;
+    __threadfence();
+    const unsigned g1 = g + 1u;
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(g1) : "memory");
+  } else {
+    unsigned now = g;
+    for (unsigned spins = 0; now == g; ++spins) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(gen) : "memory");
+      if (spins > (1u << 26)) __trap();
+      if (spins > 16) __nanosleep(64);
+    }
+  }
+  __threadfence();
+}
+
 // ------------------------------------------------------------------------------------------------
 // The scan kernel
 // ------------------------------------------------------------------------------------------------
@@ -253,6 +280,11 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   const int q_row0 = p.q_row0 + qblk * kNQ;
   const int blk_batch = p.batch - qblk * kNQ < kNQ ? p.batch - qblk * kNQ : kNQ;   // may be <= 0: idle block
   const uint64_t stream_hint = p.nblk > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+  // Tile schedule of this CTA: n_samp sample tiles (its own first tiles, scanned once more afterwards) followed
+  // by its n_my tiles first_tile, first_tile + tile_step, ...  All three roles walk the same sequence.
+  const int n_my = first_tile < p.num_tiles ? (p.num_tiles - first_tile + tile_step - 1) / tile_step : 0;
+  const int n_samp = p.sample_tiles < n_my ? p.sample_tiles : n_my;
+  const int n_iter = n_samp + n_my;
   // optional per-CTA cycle counters (diagnostics; zeroed by the host)
   const bool want_stats = p.stats != nullptr;
   unsigned long long* my_stats = want_stats ? p.stats + static_cast<size_t>(blockIdx.x) * kNumStats : nullptr;
@@ -275,7 +307,8 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = first_tile; t < p.num_tiles; t += tile_step) {
+    for (int i = 0; i < n_iter; ++i) {
+      const int t = first_tile + (i < n_samp ? i : i - n_samp) * tile_step;
       for (int si = 0; si < stages_per_tile; ++si) {
         const long long w0 = want_stats ? clock64() : 0;
         ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
@@ -305,7 +338,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     uint32_t phase = 0;
     int it = 0;
     const bool no_mma = (p.flags & kDbgNoMma) != 0;
-    for (int t = first_tile; t < p.num_tiles; t += tile_step, ++it) {
+    for (; it < n_iter; ++it) {
       const int buf = it & 1;
       long long w0 = want_stats ? clock64() : 0;
       ptx::mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
@@ -402,13 +435,89 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     // ---- per-query state lives in registers ----
     // initial threshold: the k-th best score of the sampled pre-pass when there is one (a valid
     // lower bound of the final k-th score), else -inf; dead (padding) queries never pass
-    const float seed = (p.seed && live) ? p.seed[static_cast<size_t>(qblk * kNQ + ql) * p.k + (p.k - 1)] : -INFINITY;
+    float seed = (p.seed && live) ? p.seed[static_cast<size_t>(qblk * kNQ + ql) * p.k + (p.k - 1)] : -INFINITY;
+    int it = 0;
+
+    if (p.sample_tiles > 0) {
+      // ---- phase A: the kTopJ best scores of my query over this CTA's sample tiles (registers only) ----
+      float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+      for (; it < n_samp; ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t acc = t_lane + kAccCol0 + buf * kTileN;
+        ptx::tmem_ld_32x32b_x32(acc, r0);
+        ptx::tmem_ld_32x32b_x32(acc + 32, r1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+        uint32_t pm0 = 0, pm1 = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (__uint_as_float(r0[c]) > t3) pm0 |= 1u << c;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (__uint_as_float(r1[c]) > t3) pm1 |= 1u << c;
+        const int64_t nvalid = p.n_local - static_cast<int64_t>(first_tile + it * tile_step) * kTileN;
+        if (nvalid < kTileN) {
+          const uint64_t vm = (1ull << nvalid) - 1ull;
+          pm0 &= static_cast<uint32_t>(vm);
+          pm1 &= static_cast<uint32_t>(vm >> 32);
+        }
+        while ((pm0 | pm1) != 0u) {
+          int c;
+          if (pm0 != 0u) { c = __ffs(pm0) - 1; pm0 &= pm0 - 1u; }
+          else { c = 32 + __ffs(pm1) - 1; pm1 &= pm1 - 1u; }
+          const float s = __uint_as_float(pick64(r0, r1, c));
+          if (s > t3) {
+            t3 = s;
+            if (t3 > t2) { const float x = t2; t2 = t3; t3 = x; }
+            if (t2 > t1) { const float x = t1; t1 = t2; t2 = x; }
+            if (t1 > t0) { const float x = t0; t0 = t1; t1 = x; }
+          }
+        }
+        __syncwarp();
+      }
+      if (lane_ok) {
+        uint4 v;
+        v.x = f32_to_ord(t0); v.y = f32_to_ord(t1); v.z = f32_to_ord(t2); v.w = f32_to_ord(t3);
+        reinterpret_cast<uint4*>(p.top)[static_cast<size_t>(qblk * kNQ + ql) * tile_step + first_tile] = v;
+      }
+      __threadfence();
+      ptx::named_bar_sync(3, 128);
+      if (threadIdx.x == 64) grid_sync(p.gsync, gridDim.x);
+      ptx::named_bar_sync(3, 128);
+      // ---- phase B: epilogue warp e of CTA c owns launch query c + e * grid: k-th best of all CTAs' values ----
+      {
+        const int qq = static_cast<int>(blockIdx.x) + (warp - 2) * static_cast<int>(gridDim.x);
+        if (qq < p.batch) {
+          const int nv = tile_step * kTopJ;
+          const uint32_t* src = p.top + static_cast<size_t>(qq) * nv;
+          uint32_t v[kSeedE];
+#pragma unroll
+          for (int e = 0; e < kSeedE; ++e) {
+            const int i = lane + 32 * e;
+            v[e] = i < nv ? __ldcg(src + i) : 0u;
+          }
+          const uint32_t kth = warp_kth_largest<kSeedE>(v, p.k);
+          if (lane == 0) p.seed_ord[qq] = kth;
+        }
+      }
+      __threadfence();
+      ptx::named_bar_sync(3, 128);
+      if (threadIdx.x == 64) grid_sync(p.gsync, gridDim.x);
+      ptx::named_bar_sync(3, 128);
+      if (live) seed = ord_to_f32(__ldcg(p.seed_ord + qblk * kNQ + ql));
+    }
+
     float thr = live ? seed : INFINITY;
     uint64_t thrkey = live ? (static_cast<uint64_t>(f32_to_ord(seed)) << 32) : ~0ull;
     int cnt = 0;
 
-    int it = 0;
-    for (int t = first_tile; t < p.num_tiles; t += tile_step, ++it) {
+    for (; it < n_iter; ++it) {
+      const int t = first_tile + (it - n_samp) * tile_step;
       const int buf = it & 1;
       long long w0 = want_stats ? clock64() : 0;
       ptx::mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);

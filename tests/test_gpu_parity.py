@@ -439,6 +439,38 @@ def test_in_stream_compaction_paths(eng, dev, n, b, k):
     assert rep["ok"], rep["errors"][:3]
 
 
+@pytest.mark.parametrize("n,d,b,k,dtype", [
+    (300_000, 768, 64, 100, torch.float16), (300_000, 768, 17, 128, torch.float16), (1_500_000, 768, 64, 100, torch.float16),
+    (400_000, 768, 300, 100, torch.bfloat16), (400_000, 768, 512, 37, torch.float16), (250_000, 1024, 100, 10, torch.float16),
+    (2_000_000, 256, 130, 1, torch.float16), (148 * 64 * 5 + 1, 768, 64, 100, torch.float16),
+])
+def test_in_kernel_seeding_matches_host_prepass(eng, dev, n, d, b, k, dtype):
+    """k <= 128: the sampled pre-pass runs inside the full-shard scan (top-4 per CTA and query over its first
+    tiles, grid barrier, one warp per query takes the k-th best, grid barrier).  Results must be bit-identical
+    to the separate sampled scan + select launches (debug flag 64) and to the unseeded scan (flag 4), and the
+    search must be 3 launches."""
+    e, q = _synth(n, d, b, 7 + k, dev, dtype)
+    m = _engine(eng, e, dtype)
+    s0, i0 = m.search(q, k)
+    launches = m.last_launch_count()
+    for _ in range(3):                      # the barrier words are reused by every launch
+        s0b, i0b = m.search(q, k)
+        assert torch.equal(i0, i0b) and torch.equal(s0, s0b)
+    m.debug_config(64, False)
+    s1, i1 = m.search(q, k)
+    launches_host = m.last_launch_count()
+    m.debug_config(4, False)
+    s2, i2 = m.search(q, k)
+    m.debug_config(0, False)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1), "in-kernel and host-side seeding disagree"
+    assert torch.equal(i0, i2) and torch.equal(s0, s2), "seeded and unseeded searches disagree"
+    assert launches < launches_host
+    rs, ri = _torch_ref(e, q, k, dtype)
+    exact = (q.to(dtype).double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i0.cpu().numpy(), s0.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]
+
+
 @pytest.mark.parametrize("k", [100, 700])
 def test_adversarial_row_order(eng, dev, k):
     """Scores that grow with the row number defeat the seeded thresholds (the sample is the worst part

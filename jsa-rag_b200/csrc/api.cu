@@ -31,7 +31,7 @@ struct mips_handle {
   // internal buffers
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  void* sync = nullptr;  // zero-initialised: grid barrier words | seeds of the in-kernel sampled pre-pass
+  void* sync = nullptr;  // zero-initialised: search token | per-CTA sample flags | tagged seeds (in-kernel sampled seeding)
   void* io = nullptr;  // device staging for mips_search_host: queries | scores | ids
   size_t io_bytes = 0;
   int last_launches = 0;
@@ -50,6 +50,9 @@ bool g_use_pdl = []() { const char* e = getenv("JSA_MIPS_PDL"); return !(e && e[
 }
 
 namespace {
+
+// layout of mips_handle::sync: [0] search token | kSyncFlagOff: uint32 flag per CTA | + kSyncSeedOff: uint64 seed tags
+constexpr size_t kSyncFlagOff = 256, kSyncSeedOff = 4096;
 
 std::string g_create_err;
 std::mutex g_mu;
@@ -213,7 +216,7 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
     delete h;
     return fail(nullptr, MIPS_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", h->smem_bytes, cudaGetErrorString(e));
   }
-  constexpr size_t kSyncBytes = 256 + 4 * kNQ * sizeof(uint32_t);
+  constexpr size_t kSyncBytes = kSyncFlagOff + kSyncSeedOff + 4 * kNQ * sizeof(uint64_t);
   e = cudaMalloc(&h->sync, kSyncBytes);
   if (e == cudaSuccess) e = cudaMemset(h->sync, 0, kSyncBytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -310,7 +313,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   void* qbuf = ws + w.q_off;
   const int bpad = static_cast<int>(align_up(batch, kNQ));
 
-  CUDA_TRY(h, launch_prep_queries(queries, q_dtype, q_ld, batch, bpad, h->dim, h->dtype, normalize, qbuf, st));
+  CUDA_TRY(h, launch_prep_queries(queries, q_dtype, q_ld, batch, bpad, h->dim, h->dtype, normalize, qbuf,
+                                  static_cast<uint32_t*>(h->sync), st));
   h->last_launches++;
 
   CUtensorMap tmap_q;
@@ -351,6 +355,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   // (one HBM read feeds nblk blocks through the L2), which moves large batches from HBM-bound passes
   // towards the tensor-core bound.
   constexpr int kMaxBlocks = 4;
+  int n_launch = 0;
   for (int q0 = 0; q0 < batch;) {
     int nblk = (batch - q0 + kNQ - 1) / kNQ;
     if (nblk > kMaxBlocks) nblk = kMaxBlocks;
@@ -390,18 +395,22 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       }
       for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
     }
-    // k <= 128: the last (largest) sample is scanned by the full-shard launch itself (phase A / grid barrier /
-    // phase B inside the kernel), so a search is prep + scan + select.  Needs every CTA resident (grid <= SMs, one
-    // CTA per SM), kTopJ values per list enough to cover k, and one epilogue warp per launch query for phase B.
+    // k <= 128: the last (largest) sample is scanned by the full-shard launch itself (token-tagged hand-offs inside
+    // the kernel), so a search is prep + scan + select.  Needs kTopJ values per list to cover k and one epilogue warp
+    // per launch query for the selection.
     p.sample_tiles = 0;
-    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) && launch_grid <= h->num_sms &&
-        nslots * kTopJ >= k && nslots * kTopJ <= 32 * kSeedE && launch_grid * 4 >= p.batch) {
+    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) && nslots * kTopJ >= k &&
+        nslots <= 32 * kSeedSlots && launch_grid * 4 >= p.batch && launch_grid * sizeof(uint32_t) <= kSyncSeedOff &&
+        n_launch < 64) {
       p.sample_tiles = levels[n_levels - 1];
+      p.launch_idx = n_launch;
       p.top = reinterpret_cast<uint32_t*>(ws + w.top_off);
-      p.gsync = static_cast<unsigned*>(h->sync);
-      p.seed_ord = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->sync) + 256);
+      p.token = static_cast<const uint32_t*>(h->sync);
+      p.top_flag = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->sync) + kSyncFlagOff);
+      p.seed_tag = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(h->sync) + kSyncFlagOff + kSyncSeedOff);
       n_levels = 0;
     }
+    ++n_launch;
     for (int lv = 0; lv < n_levels; ++lv) {
       ScanParams pp = p;
       pp.num_tiles = levels[lv] * nslots < num_tiles ? levels[lv] * nslots : num_tiles;

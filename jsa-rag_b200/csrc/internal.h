@@ -55,16 +55,18 @@ struct ScanParams {
   int flags;             // diagnostics: kDbgNoSelect / kDbgNoMma (results are then meaningless)
   unsigned long long* stats;  // optional [grid][kNumStats] per-CTA cycle counters (NULL = off)
   // In-kernel sampled seeding (k <= kSmallK): every CTA first scans its own first `sample_tiles` tiles keeping only
-  // the kTopJ best scores per query, the grid synchronises, one warp per query takes the k-th best of all CTAs'
-  // values (a valid lower bound of the final k-th score), the grid synchronises again and the full scan starts
-  // with that threshold.  0 = off (the thresholds come from `seed` or start at -inf).
+  // the kTopJ best scores per query, publishes them with a token-tagged flag, one warp per query takes the k-th best
+  // of all CTAs' values (a valid lower bound of the final k-th score) and publishes it with the same tag, and the
+  // full scan starts with that threshold.  0 = off (the thresholds come from `seed` or start at -inf).
   int sample_tiles;
-  uint32_t* top;         // [nblk * kNQ][grid / nblk][kTopJ] orderable score images
-  uint32_t* seed_ord;    // [nblk * kNQ] seeds produced by phase B
-  unsigned* gsync;       // {arrival count, generation}: self-resetting grid barrier
+  int launch_idx;           // scan launch number within the search (token = search token * 64 + launch_idx)
+  uint32_t* top;            // [nblk * kNQ][grid / nblk][kTopJ] orderable score images
+  uint32_t* top_flag;       // [grid] token of the launch whose samples CTA c has published
+  uint64_t* seed_tag;       // [nblk * kNQ] token << 32 | seed image
+  const uint32_t* token;    // search token, bumped by prep_queries_kernel
 };
 constexpr int kTopJ = 4;
-constexpr int kSeedE = 19;   // 32 * 19 = 608 >= 148 lists * kTopJ values handled by one warp
+constexpr int kSeedSlots = 5;   // a lane of the selecting warp looks after CTAs lane, lane + 32, ... (5 * 32 = 160 >= 148)
 
 constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
 constexpr int kDbgNoMma = 2;     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)
@@ -97,7 +99,7 @@ extern bool g_use_pdl;   // JSA_MIPS_PDL=0 disables it
 
 // launchers (defined in scan.cu / merge.cu); return cudaError_t of the launch
 cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int batch, int batch_pad, int dim,
-                                int out_dtype, int normalize, void* out, cudaStream_t st);
+                                int out_dtype, int normalize, void* out, uint32_t* token, cudaStream_t st);
 cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
                         size_t smem_bytes, cudaStream_t st);
 cudaError_t configure_scan(size_t smem_bytes);

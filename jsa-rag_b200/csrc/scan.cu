@@ -182,32 +182,28 @@ __device__ __forceinline__ uint32_t pick64(const uint32_t (&r0)[32], const uint3
   return t[0];
 }
 
-// Grid-wide barrier for the persistent scan (grid <= number of SMs, one CTA per SM, so every CTA is
-// resident).  One thread per CTA calls it.  Self-resetting: the last arriver clears the count and
-// bumps the generation the others poll, so the same two words serve every launch and graph replay.
-// Bounded: a CTA that never arrives traps the kernel instead of hanging the GPU.
-__device__ __forceinline__ void grid_sync(unsigned* gsync, unsigned n_ctas) {
-  unsigned* count = gsync;
-  unsigned* gen = gsync + 1;
-  unsigned g;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(gen) : "memory");
-  __threadfence();
-  const unsigned prev = atomicAdd(count, 1u);
-  if (prev == n_ctas - 1) {
-    *reinterpret_cast<volatile unsigned*>(count) = 0u;
-    __threadfence();
-    const unsigned g1 = g + 1u;
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(g1) : "memory");
-  } else {
-    unsigned now = g;
-    for (unsigned spins = 0; now == g; ++spins) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(gen) : "memory");
-      if (spins > (1u << 26)) __trap();
-      if (spins > 16) __nanosleep(64);
-    }
-  }
-  __threadfence();
+// Cross-CTA hand-offs of the in-kernel sampled seeding use flag words tagged with a per-launch token
+// (no counting barrier): a stale flag of an earlier launch never matches, nothing has to be reset, and
+// every wait is bounded — a CTA that is not there in time (e.g. because another kernel holds its SM) is
+// simply left out, which only makes the seed lower.  Seeds are lower bounds, so any subset is valid.
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr int kSeedOwnerSpins = 1024;    // ~0.15 ms: how long a query's owner waits for the CTAs' samples
+constexpr int kSeedReaderSpins = 4096;   // ~0.6 ms: how long a thread waits for its query's seed
 
 // ------------------------------------------------------------------------------------------------
 // The scan kernel
@@ -480,6 +476,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
         }
         __syncwarp();
       }
+      const uint32_t token = *reinterpret_cast<const volatile uint32_t*>(p.token) * 64u + static_cast<uint32_t>(p.launch_idx);
       if (lane_ok) {
         uint4 v;
         v.x = f32_to_ord(t0); v.y = f32_to_ord(t1); v.z = f32_to_ord(t2); v.w = f32_to_ord(t3);
@@ -487,29 +484,49 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       }
       __threadfence();
       ptx::named_bar_sync(3, 128);
-      if (threadIdx.x == 64) grid_sync(p.gsync, gridDim.x);
-      ptx::named_bar_sync(3, 128);
-      // ---- phase B: epilogue warp e of CTA c owns launch query c + e * grid: k-th best of all CTAs' values ----
+      if (threadIdx.x == 64) st_release_u32(p.top_flag + blockIdx.x, token);   // this CTA's samples are published
+      // ---- phase B: epilogue warp e of CTA c owns launch query c + e * grid: k-th best of the CTAs' samples ----
       {
         const int qq = static_cast<int>(blockIdx.x) + (warp - 2) * static_cast<int>(gridDim.x);
         if (qq < p.batch) {
-          const int nv = tile_step * kTopJ;
-          const uint32_t* src = p.top + static_cast<size_t>(qq) * nv;
-          uint32_t v[kSeedE];
+          const int qb = qq / kNQ;                           // lists of query block qb come from CTAs s * nblk + qb
+          bool ok[kSeedSlots];
 #pragma unroll
-          for (int e = 0; e < kSeedE; ++e) {
-            const int i = lane + 32 * e;
-            v[e] = i < nv ? __ldcg(src + i) : 0u;
+          for (int j = 0; j < kSeedSlots; ++j) ok[j] = lane + 32 * j >= tile_step;   // slots that do not exist count as done
+          for (int spins = 0; spins < kSeedOwnerSpins; ++spins) {
+            bool all = true;
+#pragma unroll
+            for (int j = 0; j < kSeedSlots; ++j) {
+              if (!ok[j]) ok[j] = ld_acquire_u32(p.top_flag + (lane + 32 * j) * p.nblk + qb) == token;
+              all = all && ok[j];
+            }
+            if (__all_sync(0xffffffffu, all)) break;
+            __nanosleep(100);
           }
-          const uint32_t kth = warp_kth_largest<kSeedE>(v, p.k);
-          if (lane == 0) p.seed_ord[qq] = kth;
+          const uint4* src = reinterpret_cast<const uint4*>(p.top) + static_cast<size_t>(qq) * tile_step;
+          const uint32_t absent = f32_to_ord(-INFINITY);    // a CTA that did not make it contributes -inf
+          uint32_t v[kSeedSlots * kTopJ];
+#pragma unroll
+          for (int j = 0; j < kSeedSlots; ++j) {
+            const int slot = lane + 32 * j;
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);               // 0 = not a candidate
+            if (slot < tile_step) x = ok[j] ? __ldcg(src + slot) : make_uint4(absent, absent, absent, absent);
+            v[4 * j + 0] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+          }
+          const uint32_t kth = warp_kth_largest<kSeedSlots * kTopJ>(v, p.k);
+          if (lane == 0) st_release_u64(p.seed_tag + qq, (static_cast<uint64_t>(token) << 32) | kth);
         }
       }
-      __threadfence();
-      ptx::named_bar_sync(3, 128);
-      if (threadIdx.x == 64) grid_sync(p.gsync, gridDim.x);
-      ptx::named_bar_sync(3, 128);
-      if (live) seed = ord_to_f32(__ldcg(p.seed_ord + qblk * kNQ + ql));
+      // ---- every thread picks up the seed of its own query (or goes on unseeded if it never arrives) ----
+      if (live) {
+        const uint64_t* mine = p.seed_tag + qblk * kNQ + ql;
+        for (int spins = 0; spins < kSeedReaderSpins; ++spins) {
+          const uint64_t tag = ld_acquire_u64(mine);
+          if (static_cast<uint32_t>(tag >> 32) == token) { seed = ord_to_f32(static_cast<uint32_t>(tag)); break; }
+          __nanosleep(100);
+        }
+      }
+      __syncwarp();
     }
 
     float thr = live ? seed : INFINITY;
@@ -661,10 +678,12 @@ __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat1
 
 template <typename TIn>
 __global__ void prep_queries_kernel(const TIn* __restrict__ q, int64_t q_ld, int batch, int dim, int out_dtype,
-                                    int normalize, void* __restrict__ out) {
+                                    int normalize, void* __restrict__ out, uint32_t* token) {
   ptx::griddep_wait();               // the query buffer may still be read by the previous search
   ptx::griddep_launch_dependents();
   const int row = blockIdx.x;
+  // one new token per search: tags the flags of the scan's in-kernel seeding (also on every graph replay)
+  if (token != nullptr && row == 0 && threadIdx.x == 0) *token = *token + 1u;
   __shared__ float red[32];
   float scale = 1.0f;
   const bool live = row < batch;
@@ -700,18 +719,18 @@ __global__ void prep_queries_kernel(const TIn* __restrict__ q, int64_t q_ld, int
 }
 
 cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int batch, int batch_pad, int dim,
-                                int out_dtype, int normalize, void* out, cudaStream_t st) {
+                                int out_dtype, int normalize, void* out, uint32_t* token, cudaStream_t st) {
   const int threads = 256;
   switch (q_dtype) {
     case 0:
       return launch_pdl(prep_queries_kernel<__half>, dim3(batch_pad), dim3(threads), 0, st, g_use_pdl,
-                        static_cast<const __half*>(q), q_ld, batch, dim, out_dtype, normalize, out);
+                        static_cast<const __half*>(q), q_ld, batch, dim, out_dtype, normalize, out, token);
     case 1:
       return launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3(batch_pad), dim3(threads), 0, st, g_use_pdl,
-                        static_cast<const __nv_bfloat16*>(q), q_ld, batch, dim, out_dtype, normalize, out);
+                        static_cast<const __nv_bfloat16*>(q), q_ld, batch, dim, out_dtype, normalize, out, token);
     default:
       return launch_pdl(prep_queries_kernel<float>, dim3(batch_pad), dim3(threads), 0, st, g_use_pdl,
-                        static_cast<const float*>(q), q_ld, batch, dim, out_dtype, normalize, out);
+                        static_cast<const float*>(q), q_ld, batch, dim, out_dtype, normalize, out, token);
   }
 }
 

@@ -471,6 +471,28 @@ def test_in_kernel_seeding_matches_host_prepass(eng, dev, n, d, b, k, dtype):
     assert rep["ok"], rep["errors"][:3]
 
 
+def test_concurrent_searches_on_two_streams(eng, dev):
+    """Two engines searching at the same time on two streams share the SMs, so neither scan has all of its CTAs
+    resident: the in-kernel seeding must not depend on that (bounded, token-tagged hand-offs; late CTAs are left
+    out and the scan proceeds with a lower seed).  Results stay exact."""
+    e1, q1 = _synth(600_000, 768, 64, 71, dev)
+    e2, q2 = _synth(500_000, 768, 48, 72, dev)
+    m1, m2 = _engine(eng, e1), _engine(eng, e2)
+    ref1, ref2 = m1.search(q1, 100), m2.search(q2, 50)
+    torch.cuda.synchronize()
+    st1, st2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    outs = []
+    for _ in range(12):
+        with torch.cuda.stream(st1):
+            outs.append((0, m1.search(q1, 100)))
+        with torch.cuda.stream(st2):
+            outs.append((1, m2.search(q2, 50)))
+    torch.cuda.synchronize()
+    for which, (s, i) in outs:
+        rs, ri = (ref1, ref2)[which]
+        assert torch.equal(i, ri) and torch.equal(s, rs)
+
+
 @pytest.mark.parametrize("k", [100, 700])
 def test_adversarial_row_order(eng, dev, k):
     """Scores that grow with the row number defeat the seeded thresholds (the sample is the worst part

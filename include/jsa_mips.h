@@ -173,6 +173,12 @@ int mips_max_rerank_candidates(void);
  */
 int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k, int normalize,
                      float* host_scores, int64_t* host_ids, void* stream);
+/* Same without the final stream synchronisation: copies and kernels are only enqueued on `stream`; host_scores /
+ * host_ids are valid once the stream (or an event recorded after the call) has completed, and host_queries must stay
+ * untouched until then.  Lets a server keep the next request in flight while it serialises the previous answer
+ * (everything stays ordered on the one stream, so no extra device buffers are involved). */
+int mips_search_host_async(mips_handle* h, const float* host_queries, int batch, int k, int normalize,
+                           float* host_scores, int64_t* host_ids, void* stream);
 
 /* Number of kernels the last mips_search_local / mips_search_host on this handle launched. */
 int mips_last_launch_count(const mips_handle* h);

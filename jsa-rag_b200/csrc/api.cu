@@ -482,8 +482,8 @@ int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void*
   return MIPS_OK;
 }
 
-int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k, int normalize, float* host_scores,
-                     int64_t* host_ids, void* stream) {
+static int search_host_impl(mips_handle* h, const float* host_queries, int batch, int k, int normalize, float* host_scores,
+                            int64_t* host_ids, void* stream, bool wait) {
   if (!h) return MIPS_EINVAL;
   h->last_launches = 0;
   if (batch < 0 || k <= 0) return fail(h, MIPS_EINVAL, "batch=%d k=%d invalid", batch, k);
@@ -510,8 +510,18 @@ int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k
   if (rc != MIPS_OK) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(host_scores, ds, static_cast<size_t>(batch) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaMemcpyAsync(host_ids, di, static_cast<size_t>(batch) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (wait) CUDA_TRY(h, cudaStreamSynchronize(st));
   return MIPS_OK;
+}
+
+int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k, int normalize, float* host_scores,
+                     int64_t* host_ids, void* stream) {
+  return search_host_impl(h, host_queries, batch, k, normalize, host_scores, host_ids, stream, true);
+}
+
+int mips_search_host_async(mips_handle* h, const float* host_queries, int batch, int k, int normalize,
+                           float* host_scores, int64_t* host_ids, void* stream) {
+  return search_host_impl(h, host_queries, batch, k, normalize, host_scores, host_ids, stream, false);
 }
 
 int mips_last_launch_count(const mips_handle* h) { return h ? h->last_launches : 0; }

@@ -99,8 +99,11 @@ class MipsEngine:
         return scores, ids
 
     def search_host(self, host_queries: torch.Tensor, k: int, normalize: bool = False,
-                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """End to end with HOST buffers (fp32 CPU tensor in, CPU tensors out): H2D + search + D2H + sync."""
+                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, wait: bool = True
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End to end with HOST buffers (fp32 CPU tensor in, CPU tensors out): H2D + search + D2H + sync.
+        ``wait=False`` only enqueues (mips_search_host_async): the outputs are valid after the current stream has
+        completed and ``host_queries`` (pinned, contiguous fp32) must stay untouched until then."""
         if host_queries.device.type != "cpu" or host_queries.dtype != torch.float32 or not host_queries.is_contiguous():
             host_queries = host_queries.detach().to("cpu", torch.float32).contiguous()
         b = int(host_queries.shape[0])
@@ -109,7 +112,9 @@ class MipsEngine:
             ids = torch.empty((b, k), dtype=torch.int64).pin_memory()
         else:
             scores, ids = out
-        rc = self._lib.mips_search_host(self._h, ctypes.cast(host_queries.data_ptr(), ctypes.POINTER(ctypes.c_float)), b,
+        fn = self._lib.mips_search_host if wait else self._lib.mips_search_host_async
+        self._async_keep = None if wait else host_queries      # a converted copy must outlive the enqueued H2D
+        rc = fn(self._h, ctypes.cast(host_queries.data_ptr(), ctypes.POINTER(ctypes.c_float)), b,
                                         int(k), int(bool(normalize)),
                                         ctypes.cast(scores.data_ptr(), ctypes.POINTER(ctypes.c_float)),
                                         ctypes.cast(ids.data_ptr(), ctypes.POINTER(ctypes.c_int64)),

@@ -471,6 +471,23 @@ def test_in_kernel_seeding_matches_host_prepass(eng, dev, n, d, b, k, dtype):
     assert rep["ok"], rep["errors"][:3]
 
 
+def test_async_host_search_keeps_requests_in_flight(eng, dev):
+    """mips_search_host_async only enqueues: several requests in flight on one stream, answers valid after the
+    event recorded behind each of them, identical to the synchronous call."""
+    e, q = _synth(200_000, 768, 40, 81, dev)
+    m = _engine(eng, e)
+    qs = [torch.roll(q, r, 0).cpu().pin_memory() for r in range(4)]
+    want = [m.search_host(x, 20) for x in qs]
+    outs = [(torch.empty(40, 20).pin_memory(), torch.empty(40, 20, dtype=torch.int64).pin_memory()) for _ in qs]
+    evs = []
+    for x, o in zip(qs, outs):
+        m.search_host(x, 20, out=o, wait=False)
+        ev = torch.cuda.Event(); ev.record(); evs.append(ev)
+    for ev, o, w in zip(evs, outs, want):
+        ev.synchronize()
+        assert torch.equal(o[1], w[1]) and torch.equal(o[0], w[0])
+
+
 def test_concurrent_searches_on_two_streams(eng, dev):
     """Two engines searching at the same time on two streams share the SMs, so neither scan has all of its CTAs
     resident: the in-kernel seeding must not depend on that (bounded, token-tagged hand-offs; late CTAs are left

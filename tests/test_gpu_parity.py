@@ -446,14 +446,13 @@ def test_in_stream_compaction_paths(eng, dev, n, b, k):
 ])
 def test_in_kernel_seeding_matches_host_prepass(eng, dev, n, d, b, k, dtype):
     """k <= 128: the sampled pre-pass runs inside the full-shard scan (top-4 per CTA and query over its first
-    tiles, grid barrier, one warp per query takes the k-th best, grid barrier).  Results must be bit-identical
-    to the separate sampled scan + select launches (debug flag 64) and to the unseeded scan (flag 4), and the
-    search must be 3 launches."""
+    tiles, token-tagged flags, one warp per query takes the k-th best).  Results must be bit-identical to the
+    separate sampled scan + select launches (debug flag 64) and to the unseeded scan (flag 4), with fewer launches."""
     e, q = _synth(n, d, b, 7 + k, dev, dtype)
     m = _engine(eng, e, dtype)
     s0, i0 = m.search(q, k)
     launches = m.last_launch_count()
-    for _ in range(3):                      # the barrier words are reused by every launch
+    for _ in range(3):                      # the flag words are reused by every launch (fresh token each time)
         s0b, i0b = m.search(q, k)
         assert torch.equal(i0, i0b) and torch.equal(s0, s0b)
     m.debug_config(64, False)

@@ -396,10 +396,11 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       for (int i = nt - 1; i >= 0; --i) levels[n_levels++] = tmp[i];
     }
     // k <= 128: the last (largest) sample is scanned by the full-shard launch itself (token-tagged hand-offs inside
-    // the kernel), so a search is prep + scan + select.  Needs kTopJ values per list to cover k and one epilogue warp
-    // per launch query for the selection.
+    // the kernel), so a search is prep + scan + select.  Needs one epilogue warp per launch query for the selection
+    // and 4x more per-CTA values than k: with fewer (large batches split the CTAs over 2-4 query blocks) the top-kTopJ
+    // truncation loosens the seed and the separate sampled launches win (measured at batch 1024: 48.3 vs 49.5 ms).
     p.sample_tiles = 0;
-    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) && nslots * kTopJ >= k &&
+    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) && nslots * kTopJ >= 4 * k &&
         nslots <= 32 * kSeedSlots && launch_grid * 4 >= p.batch && launch_grid * sizeof(uint32_t) <= kSyncSeedOff &&
         n_launch < 64) {
       p.sample_tiles = levels[n_levels - 1];

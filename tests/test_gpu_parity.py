@@ -463,7 +463,7 @@ def test_in_kernel_seeding_matches_host_prepass(eng, dev, n, d, b, k, dtype):
     m.debug_config(0, False)
     assert torch.equal(i0, i1) and torch.equal(s0, s1), "in-kernel and host-side seeding disagree"
     assert torch.equal(i0, i2) and torch.equal(s0, s2), "seeded and unseeded searches disagree"
-    assert launches < launches_host
+    assert launches <= launches_host and (b > 128 or launches == 3)
     rs, ri = _torch_ref(e, q, k, dtype)
     exact = (q.to(dtype).double() @ e.double().T).cpu().numpy()
     rep = O.compare_topk(i0.cpu().numpy(), s0.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)

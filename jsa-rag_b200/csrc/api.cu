@@ -223,7 +223,7 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
   if (e != cudaSuccess) {
     if (h->sync) cudaFree(h->sync);
     delete h;
-    return fail(nullptr, MIPS_ECUDA, "allocating the barrier words failed: %s", cudaGetErrorString(e));
+    return fail(nullptr, MIPS_ECUDA, "allocating the seeding flag words failed: %s", cudaGetErrorString(e));
   }
   *out = h;
   return MIPS_OK;

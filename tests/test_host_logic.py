@@ -204,3 +204,23 @@ def test_filter_results_by_id(eng):
     assert [d["id"] for d in p[0]] == ["a", "c", "d", "b"] and list(s[0]) == [4.0, 2.0, 1.0, 3.0]
     p, s = eng.filter_results_by_id(None, docs, scores, 3)           # padding instance: plain cut
     assert [len(r) for r in p] == [3, 3] and s[1] == [8.0, 7.0, 6.0]
+
+
+def test_peer_exchange_is_optional_and_never_a_cpu_path(eng, monkeypatch):
+    """Without an NCCL process group (single process, gloo, CPU) no exchange object is created — callers keep the
+    collective path — and the mode switch is read from the environment."""
+    import importlib
+    ex = importlib.import_module("jsa-rag_b200.exchange")
+    assert ex.make_peer_exchange("cpu", 1 << 20) is None
+    monkeypatch.setenv("JSA_MIPS_EXCHANGE", "nccl")
+    assert ex.exchange_mode() == "nccl"
+    monkeypatch.delenv("JSA_MIPS_EXCHANGE")
+    assert ex.exchange_mode() == "p2p"
+    lib = eng._native.load()
+    assert lib.mips_xchg_handle_bytes() == 64
+    # argument validation happens before any CUDA call
+    import ctypes
+    h = ctypes.c_void_p()
+    assert lib.mips_xchg_create(ctypes.byref(h), 0, 3, 2, 1024) == eng._native.MIPS_EINVAL      # rank >= world
+    assert lib.mips_xchg_create(ctypes.byref(h), 0, 0, 17, 1024) == eng._native.MIPS_EINVAL     # world > 16
+    assert lib.mips_xchg_merge(None, None, 0, 0, 1, 1, 1, None, None, None) == eng._native.MIPS_EINVAL

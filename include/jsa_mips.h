@@ -40,6 +40,7 @@ extern "C" {
 #define MIPS_ENOTBOUND (-4)   /* search before mips_bind_index */
 #define MIPS_EWORKSPACE (-5)  /* caller-provided workspace too small */
 #define MIPS_EUNSUPPORTED (-6)/* not running on an sm_100 device / feature not built */
+#define MIPS_ETIMEOUT    (-7) /* peer exchange: a rank's block did not arrive within the exchange timeout */
 
 typedef struct mips_handle mips_handle;
 
@@ -148,6 +149,24 @@ int mips_xchg_merge(mips_xchg* x, const void* local_block, size_t block_bytes, s
 /* Plain all-gather over the same mechanism (the query all-gather of src/index.py:128): every rank's `block_bytes`
  * (equal on all ranks, multiple of 8) -> out [W, block_bytes] in rank order on every rank.  Two launches. */
 int mips_xchg_gather(mips_xchg* x, const void* local_block, size_t block_bytes, void* out, void* stream);
+/* The two halves of mips_xchg_merge / mips_xchg_gather as separate calls (one launch each): a rank may push as soon
+ * as its block is ready and wait later.  Every push must be followed by exactly one *_wait before the next push. */
+int mips_xchg_push(mips_xchg* x, const void* local_block, size_t block_bytes, void* stream);
+int mips_xchg_merge_wait(mips_xchg* x, size_t block_bytes, size_t score_bytes, int batch, int k_in, int k_out,
+                         float* out_scores, int64_t* out_ids, void* stream);
+int mips_xchg_gather_wait(mips_xchg* x, size_t block_bytes, void* out, void* stream);
+/* Stragglers: the receiving kernels wait for the peers' blocks in wall-clock time — 30 minutes by default (the order
+ * of a collective watchdog; the reference tolerates 100000 s, src/slurm.py:181), JSA_MIPS_XCHG_TIMEOUT_S or
+ * mips_xchg_set_timeout_ms change it.  On expiry nothing traps: the kernel writes padding (score -inf, id -1; a
+ * gather leaves `out` untouched), raises a host-visible error word, and this and every later call on the exchange
+ * returns MIPS_ETIMEOUT (mips_xchg_status reads the word without launching anything).  The CUDA context stays usable;
+ * the caller tears the exchange down and falls back to the all-gather path. */
+int mips_xchg_set_timeout_ms(mips_xchg* x, int64_t ms);
+int mips_xchg_status(mips_xchg* x);
+/* Test wiring: connects W exchanges that live in ONE process on ONE device by their device pointers (no IPC), so
+ * that the push / merge / gather kernels can be driven rank by rank on a single GPU: launch all W pushes of a step
+ * first, then the W waits (a wait launched before its peers' pushes would only sit out its timeout). */
+int mips_xchg_connect_local(mips_xchg* x, mips_xchg* const* all, int n);
 const char* mips_xchg_last_error(mips_xchg* x);
 int mips_xchg_destroy(mips_xchg* x);
 
@@ -187,7 +206,8 @@ int mips_last_launch_count(const mips_handle* h);
  * Diagnostics (not used on the product path).  flags: 1 = skip the select epilogue, 2 = skip the
  * MMAs (pure TMA streaming) — results are meaningless with either set; 4 = no sampled pre-pass;
  * 8 = time the scan launches; 16 = always UMMA M=128; 32 = one query block per launch; 64 = seed the thresholds
- * with separate sampled scan + select launches instead of inside the scan kernel.  stats_dev: device array of
+ * with separate sampled scan + select launches instead of inside the scan kernel; 128 = batches > 128 without
+ * tcgen05 CTA pairs (the round-1 multi-block path).  stats_dev: device array of
  * [mips_num_sms()][mips_debug_num_stats()] uint64 per-CTA cycle counters the scan kernel fills
  * (caller zeroes it), or NULL.  Counter order: producer wait, MMA wait(full), MMA wait(TMEM),
  * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles.

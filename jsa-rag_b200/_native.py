@@ -2,7 +2,7 @@
 
 There is deliberately no fallback: if the shared library has not been built, or no sm_100 device
 is present, every entry point raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
-or ``make -C jsa-rag_b200/csrc``.
+(or ``python jsa-rag_b200/build.py --force -v``).
 """
 from __future__ import annotations
 
@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libjsa_mips.so")
 
 MIPS_DTYPE_F16, MIPS_DTYPE_BF16, MIPS_DTYPE_F32 = 0, 1, 2
 MIPS_OK, MIPS_EINVAL, MIPS_EKRANGE, MIPS_ECUDA, MIPS_ENOTBOUND, MIPS_EWORKSPACE, MIPS_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+MIPS_ETIMEOUT = -7
 
 # every symbol include/jsa_mips.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -43,6 +44,12 @@ SYMBOLS = {
     "mips_xchg_capacity": (c_size_t, [c_void_p]),
     "mips_xchg_merge": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mips_xchg_gather": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mips_xchg_push": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mips_xchg_merge_wait": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mips_xchg_gather_wait": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mips_xchg_set_timeout_ms": (c_int, [c_void_p, c_int64]),
+    "mips_xchg_status": (c_int, [c_void_p]),
+    "mips_xchg_connect_local": (c_int, [c_void_p, POINTER(c_void_p), c_int]),
     "mips_xchg_last_error": (c_char_p, [c_void_p]),
     "mips_xchg_destroy": (c_int, [c_void_p]),
     "mips_search_host": (c_int, [c_void_p, POINTER(c_float), c_int, c_int, c_int, POINTER(c_float), POINTER(c_int64),

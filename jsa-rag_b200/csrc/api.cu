@@ -24,10 +24,14 @@ struct mips_handle {
   int64_t n_local = 0, ld = 0, id_base = 0, id_stride = 1;
   int layout = 1;   // 1: [n_local, dim] K-major rows; 0: [dim, n_local] (the reference's layout, MN-major operand)
   CUtensorMap tmap_e;
+  CUtensorMap tmap_e_half;   // boxes of kTileN / 2 passages: what each CTA of a tcgen05 pair loads per tile
   bool bound = false;
   // kernel geometry
   int num_kchunks = 0, num_stages = 0, chunks_per_stage = 2;
   size_t smem_bytes = 0;
+  // CTA-pair kernel (batches > 128): stages of half tiles, pairs the device keeps resident
+  int pair_stages = 0, max_pairs = 0;
+  size_t pair_smem_bytes = 0;
   // internal buffers
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -107,22 +111,6 @@ struct DeviceGuard {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Row-major [rows, dim] 16-bit matrix -> 2-D tensor map, box = {64 elements (128 B), box_rows},
-// 128-byte swizzle, zero fill out of bounds.
-int encode_rows_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t rows, int64_t ld, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->dim), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKChunk), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUtensorMapDataType dt = h->dtype == MIPS_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(h, MIPS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return MIPS_OK;
-}
-
 // Generic row-major [rows, cols] 16-bit matrix -> 2-D tensor map with box {64 cols (128 B), box_rows}.
 int encode_2d_map(mips_handle* h, CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -144,16 +132,16 @@ struct WsLayout {
 
 WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
   WsLayout w;
-  const size_t bpad = align_up(static_cast<size_t>(max_batch > 0 ? max_batch : 1), kNQ);
+  const size_t bpad = align_up(static_cast<size_t>(max_batch > 0 ? max_batch : 1), 2 * kNQ);   // whole CTA pairs
   const size_t grid = static_cast<size_t>(h->num_sms);
   const size_t cap = max_k <= kSmallK ? kCap : kCapBig;
   size_t off = 0;
   w.q_off = off;    off += align_up(bpad * h->dim * 2, 1024);
   w.cand_off = off; off += align_up(grid * kNQ * cap * sizeof(uint64_t), 1024);
   w.pk_off = off;   off += align_up(grid * kNQ * sizeof(int), 1024);
-  w.seed_s_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * max_k * sizeof(float), 1024);
-  w.seed_i_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * max_k * sizeof(int64_t), 1024);
-  w.top_off = off; off += align_up(static_cast<size_t>(4 * kNQ) * grid * kTopJ * sizeof(uint32_t), 1024);
+  w.seed_s_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * max_k * sizeof(float), 1024);
+  w.seed_i_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * max_k * sizeof(int64_t), 1024);
+  w.top_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * grid * kTopJ * sizeof(uint32_t), 1024);
   w.total = off;
   return w;
 }
@@ -211,12 +199,26 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
   h->num_stages = stages;
   h->chunks_per_stage = cps;
   h->smem_bytes = 1024 + q_bytes + static_cast<size_t>(stages) * stage_bytes + kCtrlBytes;
-  cudaError_t e = configure_scan(h->smem_bytes);
+  cudaError_t e = configure_scan();
   if (e != cudaSuccess) {
     delete h;
-    return fail(nullptr, MIPS_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", h->smem_bytes, cudaGetErrorString(e));
+    return fail(nullptr, MIPS_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", kMaxSmem, cudaGetErrorString(e));
   }
-  constexpr size_t kSyncBytes = kSyncFlagOff + kSyncSeedOff + 4 * kNQ * sizeof(uint64_t);
+  // CTA-pair kernel: every CTA loads half tiles (32 passages x the whole K extent per stage), so twice as many
+  // stages fit; the pair count comes from the occupancy query (74 on a full B200: every TPC holds one pair)
+  {
+    const int half_stage = h->num_kchunks * (kChunkBytes / 2);
+    int ps = (kMaxSmem - 1024 - kCtrlBytes - q_bytes) / half_stage;
+    if (ps > kMaxStages) ps = kMaxStages;
+    if (const char* e2 = getenv("JSA_MIPS_PAIR_STAGES")) { const int v = atoi(e2); if (v >= 2 && v < ps) ps = v; }
+    h->pair_stages = ps;
+    h->pair_smem_bytes = 1024 + q_bytes + static_cast<size_t>(ps) * half_stage + kCtrlBytes;
+    int np = 0;
+    if (ps >= 2 && max_resident_pairs(h->pair_smem_bytes, &np) == cudaSuccess) h->max_pairs = np;
+    cudaGetLastError();
+    if (const char* e2 = getenv("JSA_MIPS_PAIRS")) { if (e2[0] == '0') h->max_pairs = 0; }
+  }
+  constexpr size_t kSyncBytes = kSyncFlagOff + kSyncSeedOff + kMaxQBlocks * kNQ * sizeof(uint64_t);
   e = cudaMalloc(&h->sync, kSyncBytes);
   if (e == cudaSuccess) e = cudaMemset(h->sync, 0, kSyncBytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -263,6 +265,10 @@ int mips_bind_index_layout(mips_handle* h, const void* emb, int64_t n_local, int
     int rc = layout == 1 ? encode_2d_map(h, &h->tmap_e, emb, n_local, h->dim, ld, kTileN)
                          : encode_2d_map(h, &h->tmap_e, emb, h->dim, n_local, ld, kKChunk);
     if (rc != MIPS_OK) return rc;
+    if (layout == 1) {
+      rc = encode_2d_map(h, &h->tmap_e_half, emb, n_local, h->dim, ld, kTileN / 2);
+      if (rc != MIPS_OK) return rc;
+    }
   }
   h->bound = true;
   return MIPS_OK;
@@ -292,6 +298,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   if (q_dtype < 0 || q_dtype > 2) return fail(h, MIPS_EINVAL, "q_dtype=%d invalid", q_dtype);
   if (q_ld < h->dim) return fail(h, MIPS_EINVAL, "q_ld=%lld < dim", (long long)q_ld);
   DeviceGuard g(h->device);
+  if (!g.ok) return fail(h, MIPS_ECUDA, "cudaSetDevice(%d) failed", h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const WsLayout w = ws_layout(h, batch, k);
@@ -311,14 +318,14 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     ws = static_cast<uint8_t*>(h->ws);
   }
   void* qbuf = ws + w.q_off;
-  const int bpad = static_cast<int>(align_up(batch, kNQ));
+  const int bpad = static_cast<int>(align_up(batch, 2 * kNQ));
 
   CUDA_TRY(h, launch_prep_queries(queries, q_dtype, q_ld, batch, bpad, h->dim, h->dtype, normalize, qbuf,
                                   static_cast<uint32_t*>(h->sync), st));
   h->last_launches++;
 
   CUtensorMap tmap_q;
-  int rc = encode_rows_map(h, &tmap_q, qbuf, bpad, h->dim, kNQ);
+  int rc = encode_2d_map(h, &tmap_q, qbuf, bpad, h->dim, h->dim, kNQ);
   if (rc != MIPS_OK) return rc;
 
   const int num_tiles = static_cast<int>((h->n_local + kTileN - 1) / kTileN);
@@ -342,11 +349,6 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   p.flags = h->dbg_flags;
   p.stats = h->dbg_stats;
 
-  // Sampled pre-passes.  The k-th best score of any sample of the shard is a valid lower bound of
-  // the final k-th score, so it can seed the thresholds of a larger pass, which then appends only
-  // ~k * tiles / (grid * sample_tiles) candidates per (CTA, query): few enough that no list is ever
-  // compacted in-stream and the select kernel takes the raw lists.  levels[] holds the tiles per CTA
-  // of each pre-pass (the first is unseeded and one tile deep, so its lists hold <= 128 entries).
   float* seed_scores = reinterpret_cast<float*>(ws + w.seed_s_off);
   int64_t* seed_ids = reinterpret_cast<int64_t*>(ws + w.seed_i_off);
 
@@ -354,22 +356,45 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   // blocks per launch the CTAs split into nblk groups that scan the same tile sequence side by side
   // (one HBM read feeds nblk blocks through the L2), which moves large batches from HBM-bound passes
   // towards the tensor-core bound.
+  //
+  // More than 128 queries left: tcgen05 CTA pairs (cta_group::2, UMMA M = 256).  A pair serves 256 queries and each
+  // of its CTAs loads only half of every passage tile, which halves the shared-memory fill per unit of tensor work;
+  // one launch carries 1 or 2 pair blocks (256 / 512 queries; with 74 pairs, 2 blocks x 37 tile sequences).
   constexpr int kMaxBlocks = 4;
+  const bool pairs_ok = h->layout == 1 && h->max_pairs >= 1 && !(h->dbg_flags & (kDbgNoPair | kDbgOneBlock));
   int n_launch = 0;
   for (int q0 = 0; q0 < batch;) {
-    int nblk = (batch - q0 + kNQ - 1) / kNQ;
-    if (nblk > kMaxBlocks) nblk = kMaxBlocks;
-    if (nblk == 3) nblk = 2;                       // grid (148) must divide evenly
-    if (h->dbg_flags & kDbgOneBlock) nblk = 1;
-    const int launch_grid = grid >= nblk ? (grid / nblk) * nblk : nblk;   // tiny indices: surplus CTAs just idle
+    const int rem = batch - q0;
+    const bool pair = pairs_ok && rem > kNQ;
+    int nblk, launch_grid;
+    if (pair) {
+      // pair blocks of this launch: 4 (1024 queries per pass over the index) halve the HBM/L2 traffic per flop
+      // once more, at the price of 2 idle pairs of 74 (72 = 4 x 18 tile sequences)
+      static const int max_npb = []() { const char* e = getenv("JSA_MIPS_PAIR_BLOCKS"); const int v = e ? atoi(e) : 4; return v == 4 ? 4 : (v == 1 ? 1 : 2); }();
+      int npb = rem > 4 * kNQ && max_npb >= 4 ? 4 : (rem > 2 * kNQ && max_npb >= 2 ? 2 : 1);
+      nblk = 2 * npb;
+      int pairs = grid / 2 < h->max_pairs ? grid / 2 : h->max_pairs;
+      launch_grid = pairs >= npb ? (pairs / npb) * nblk : nblk;    // tiny indices: surplus pairs just idle
+    } else {
+      nblk = (rem + kNQ - 1) / kNQ;
+      if (nblk > kMaxBlocks) nblk = kMaxBlocks;
+      if (nblk == 3) nblk = 2;                       // grid (148) must divide evenly
+      if (h->dbg_flags & kDbgOneBlock) nblk = 1;
+      launch_grid = grid >= nblk ? (grid / nblk) * nblk : nblk;   // tiny indices: surplus CTAs just idle
+    }
     const int nslots = launch_grid / nblk;         // CTAs (= candidate lists) per query block
     p.nblk = nblk;
-    p.batch = batch - q0 < kNQ * nblk ? batch - q0 : kNQ * nblk;
+    p.batch = rem < kNQ * nblk ? rem : kNQ * nblk;
     p.q_row0 = q0;
     p.seed = nullptr;
-    p.m64 = (nblk == 1 && p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
-    p.idesc = ptx::make_idesc_f16(p.m64 ? 64 : kNQ, kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0) |
+    p.m64 = (!pair && nblk == 1 && p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
+    p.idesc = ptx::make_idesc_f16(pair ? 2 * kNQ : (p.m64 ? 64 : kNQ), kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0) |
               (p.b_mn ? (1u << 16) : 0u);   // bit 16: B operand is MN-major
+    p.num_stages = pair ? h->pair_stages : h->num_stages;
+    p.chunks_per_stage = pair ? h->num_kchunks : h->chunks_per_stage;
+    const CUtensorMap& tmap_e = pair ? h->tmap_e_half : h->tmap_e;
+    const size_t smem_bytes = pair ? h->pair_smem_bytes : h->smem_bytes;
+    auto scan = pair ? launch_scan_pair : launch_scan;
 
     // Sampled pre-passes.  The k-th best score of any sample of the shard is a valid lower bound of
     // the final k-th score, so it can seed the thresholds of a larger pass, which then appends only
@@ -416,14 +441,14 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       ScanParams pp = p;
       pp.num_tiles = levels[lv] * nslots < num_tiles ? levels[lv] * nslots : num_tiles;
       pp.stats = nullptr;
-      CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, pp, launch_grid, h->smem_bytes, st));
+      CUDA_TRY(h, scan(tmap_e, tmap_q, pp, launch_grid, smem_bytes, st));
       CUDA_TRY(h, launch_select(p.cand, p.part_cnt, nslots, nblk, p.cap, p.batch, k, 0, 1, seed_scores, seed_ids, st));
       h->last_launches += 2;
       p.seed = seed_scores;
     }
     const bool timed = (h->dbg_flags & kDbgTimeScan) && h->timing_ready && h->n_timed < mips_handle::kMaxTimed;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev0[h->n_timed], st));
-    CUDA_TRY(h, launch_scan(h->tmap_e, tmap_q, p, launch_grid, h->smem_bytes, st));
+    CUDA_TRY(h, scan(tmap_e, tmap_q, p, launch_grid, smem_bytes, st));
     if (timed) { CUDA_TRY(h, cudaEventRecord(h->ev1[h->n_timed], st)); h->n_timed++; }
     CUDA_TRY(h, launch_select(p.cand, p.part_cnt, nslots, nblk, p.cap, p.batch, k, h->id_base, h->id_stride,
                               out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
@@ -479,6 +504,7 @@ int mips_gather_rows(mips_handle* h, const int64_t* local_rows, int64_t n, void*
   if (!h->bound) return fail(h, MIPS_ENOTBOUND, "mips_bind_index has not been called");
   if (n < 0 || (n > 0 && (!local_rows || !out))) return fail(h, MIPS_EINVAL, "bad gather arguments");
   DeviceGuard g(h->device);
+  if (!g.ok) return fail(h, MIPS_ECUDA, "cudaSetDevice(%d) failed", h->device);
   CUDA_TRY(h, launch_gather_rows(h->emb, h->ld, h->dim, h->n_local, h->layout, local_rows, n, out, static_cast<cudaStream_t>(stream)));
   return MIPS_OK;
 }

@@ -14,6 +14,7 @@ constexpr int kKChunk = 64;      // elements per K chunk: 64 x 2 B = one 128-byt
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
 constexpr int kChunkBytes = kTileN * kKChunk * 2;                 // 8 KiB: [64 passages x 64 el], SWIZZLE_128B
 constexpr int kQChunkBytes = kNQ * kKChunk * 2;                   // 16 KiB: [128 queries x 64 el] (smem-resident K tail)
+constexpr int kMaxQBlocks = 8;   // query blocks (of kNQ) one launch can carry: 4 single CTAs or 4 CTA pairs
 constexpr int kMaxStages = 12;
 constexpr int kTmemCols = 512;   // whole TMEM: queries (A operand) + two accumulator buffers
 constexpr int kAccCol0 = kTmemCols - 2 * kTileN;                  // accumulators live in the last 128 columns
@@ -39,7 +40,8 @@ struct ScanParams {
   int chunks_per_stage;  // K chunks (8 KiB each) one pipeline stage carries
   int k;                 // top-k (<= kMaxK)
   int batch;             // valid queries in this launch (<= kNQ * nblk)
-  int nblk;              // query blocks scanned concurrently by this launch (1, 2 or 4; grid % nblk == 0)
+  int nblk;              // query blocks (of kNQ) scanned concurrently by this launch (1, 2 or 4; grid % nblk == 0);
+                         // CTA c serves block c % nblk — in the pair kernel CTAs 2j, 2j+1 are one tcgen05 CTA pair
   int m64;               // 1: UMMA M=64 (batch <= 64), 0: UMMA M=128
   int b_mn;              // 1: index stored [dim, n_local] (MN-major B operand), 0: [n_local, dim] (K-major)
   int q_row0;            // first row of this pass in the prepared query buffer
@@ -60,7 +62,7 @@ struct ScanParams {
   // full scan starts with that threshold.  0 = off (the thresholds come from `seed` or start at -inf).
   int sample_tiles;
   int launch_idx;           // scan launch number within the search (token = search token * 64 + launch_idx)
-  uint32_t* top;            // [nblk * kNQ][grid / nblk][kTopJ] orderable score images
+  uint32_t* top;            // [nblk * kNQ][grid / nblk][kTopJ] orderable score images (nblk <= kMaxQBlocks)
   uint32_t* top_flag;       // [grid] token of the launch whose samples CTA c has published
   uint64_t* seed_tag;       // [nblk * kNQ] token << 32 | seed image
   const uint32_t* token;    // search token, bumped by prep_queries_kernel
@@ -75,8 +77,10 @@ constexpr int kDbgForceM128 = 16; // always use UMMA M=128 (A/B test of the M=64
 constexpr int kDbgOneBlock = 32;  // one query block per launch even for large batches (A/B test of the L2-shared multi-block scan)
 constexpr int kDbgHostPrepass = 64; // seed thresholds with separate sampled scan + select launches (the pre-fusion path; always used for k > 128)
 constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
+constexpr int kDbgNoTma = 256;   // the producer hands over stages without loading them (power/latency split; results meaningless)
+constexpr int kDbgNoPair = 128;  // batches > 128 without tcgen05 CTA pairs (the round-1 multi-block path; A/B test)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
-            kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kStEpiBar, kNumStats };
+            kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kNumStats };
 
 // Launch helper: programmatic dependent launch lets the prologue of kernel N+1 (barrier init, TMEM
 // allocation, the first TMA loads of the static index) overlap the tail of kernel N.
@@ -102,7 +106,10 @@ cudaError_t launch_prep_queries(const void* q, int q_dtype, int64_t q_ld, int ba
                                 int out_dtype, int normalize, void* out, uint32_t* token, cudaStream_t st);
 cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
                         size_t smem_bytes, cudaStream_t st);
-cudaError_t configure_scan(size_t smem_bytes);
+cudaError_t launch_scan_pair(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
+                             size_t smem_bytes, cudaStream_t st);
+cudaError_t max_resident_pairs(size_t smem_bytes, int* out);
+cudaError_t configure_scan();
 cudaError_t launch_merge(const float* scores, const int64_t* ids, int num_lists, int64_t list_stride,
                          int64_t id_list_stride, int batch, int k_in, int k_out, float* out_scores, int64_t* out_ids,
                          cudaStream_t st);
@@ -125,9 +132,42 @@ static_assert(sizeof(XchgCtrl) <= kXchgCtrlBytes, "control block too large");
 struct XchgPeers { uint8_t* base[kXchgMaxWorld]; };
 cudaError_t launch_xchg_push(const XchgPeers& peers, int rank, int world, const void* local_block, size_t block_bytes,
                              size_t cap, cudaStream_t st);
-cudaError_t launch_xchg_gather(uint8_t* local_base, int world, size_t cap, size_t block_bytes, void* out, cudaStream_t st);
+cudaError_t launch_xchg_gather(uint8_t* local_base, int world, size_t cap, size_t block_bytes, void* out,
+                               unsigned long long timeout_ns, int* err_word, cudaStream_t st);
 cudaError_t launch_xchg_merge(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int batch, int k_in, int k_out,
-                              float* out_scores, int64_t* out_ids, cudaStream_t st);
+                              float* out_scores, int64_t* out_ids, unsigned long long timeout_ns, int* err_word,
+                              cudaStream_t st);
+
+#ifdef __CUDACC__
+// Block-wide wait of the receiving kernels: thread p < world polls flag[slot][p] until it carries `epoch`.  The
+// bound is wall-clock time (%globaltimer); on expiry the host-mapped error word is set and false is returned to the
+// whole block — the caller writes padding / nothing and returns, the CUDA context stays usable.
+__device__ __forceinline__ bool xchg_wait_flags(XchgCtrl* ctrl, int slot, unsigned long long epoch, int world,
+                                                unsigned long long timeout_ns, int* err_word) {
+  int late = 0;
+  if (threadIdx.x < world) {
+    const unsigned long long* flag = &ctrl->flags[slot][threadIdx.x];
+    unsigned long long seen = 0, t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (seen >= epoch) break;
+      if ((spins & 1023u) == 1023u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) { late = 1; break; }
+      }
+      __nanosleep(spins < 64 ? 20 : (spins < 4096 ? 200 : 2000));
+    }
+  }
+  late = __syncthreads_or(late);
+  if (late && threadIdx.x == 0 && err_word != nullptr) {
+    *reinterpret_cast<volatile int*>(err_word) = 1;
+    __threadfence_system();
+  }
+  return late == 0;
+}
+#endif
 
 cudaError_t launch_rerank(const void* q, int64_t q_ld, const void* cand, int dtype, int batch, int num_cand, int dim,
                           int k, float* out_scores, int64_t* out_pos, int64_t* out_rank, void* out_emb, cudaStream_t st);

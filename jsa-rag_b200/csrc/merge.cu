@@ -155,26 +155,24 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
 
 // Fused exchange + merge, receiving half: the W candidate blocks of this step were (or are being) stored into
 // this GPU's exchange slot by the peers' xchg_push_kernel over NVLink.  Every CTA waits until all W arrival flags
-// carry this step's epoch, then merges straight out of the slot.  The wait is bounded: a peer that never pushes
-// traps this kernel (an error the host sees) instead of hanging the GPU.
+// carry this step's epoch, then merges straight out of the slot.  The wait is bounded in wall-clock time (host-set,
+// minutes by default): a peer that never pushes makes this kernel write padding and raise the exchange's error word
+// (the next call on the exchange fails with MIPS_ETIMEOUT); nothing traps, the context stays alive.
 template <int kMergeE>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 xchg_merge_kernel(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int k_in, int k_out,
-                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids, unsigned long long timeout_ns,
+                  int* err_word) {
   XchgCtrl* ctrl = reinterpret_cast<XchgCtrl*>(local_base);
   const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(&ctrl->epoch);   // set by our own push
   const int slot = static_cast<int>((epoch - 1) & 1);
-  if (threadIdx.x < world) {
-    const unsigned long long* flag = &ctrl->flags[slot][threadIdx.x];
-    unsigned long long seen = 0;
-    for (unsigned spins = 0;; ++spins) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-      if (seen >= epoch) break;
-      if (spins > (1u << 26)) __trap();
-      __nanosleep(spins < 64 ? 20 : 200);
+  if (!xchg_wait_flags(ctrl, slot, epoch, world, timeout_ns, err_word)) {
+    for (int pos = threadIdx.x; pos < k_out; pos += blockDim.x) {
+      out_scores[static_cast<int64_t>(blockIdx.x) * k_out + pos] = -INFINITY;
+      out_ids[static_cast<int64_t>(blockIdx.x) * k_out + pos] = -1;
     }
+    return;
   }
-  __syncthreads();
   const uint8_t* slot_base = local_base + kXchgCtrlBytes + static_cast<size_t>(slot) * world * cap;
   merge_lists<kMergeE>(reinterpret_cast<const float*>(slot_base), reinterpret_cast<const int64_t*>(slot_base + s_bytes), world,
                        static_cast<int64_t>(cap / 4), static_cast<int64_t>(cap / 8), k_in, k_out, out_scores, out_ids);
@@ -569,20 +567,23 @@ cudaError_t configure_merge() {
 }
 
 cudaError_t launch_xchg_merge(uint8_t* local_base, int world, size_t cap, size_t s_bytes, int batch, int k_in, int k_out,
-                              float* out_scores, int64_t* out_ids, cudaStream_t st) {
+                              float* out_scores, int64_t* out_ids, unsigned long long timeout_ns, int* err_word,
+                              cudaStream_t st) {
   if (batch == 0) return cudaSuccess;
   const int kk = k_in > k_out ? k_in : k_out;
   if (kk <= kSmallK) {
     constexpr int E = kSmallK / 32;
     const size_t smem = static_cast<size_t>(kMergeWarps) * 32 * E * (sizeof(int64_t) + sizeof(uint32_t));
-    xchg_merge_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(local_base, world, cap, s_bytes, k_in, k_out, out_scores, out_ids);
+    xchg_merge_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(local_base, world, cap, s_bytes, k_in, k_out, out_scores, out_ids,
+                                                                timeout_ns, err_word);
     return cudaGetLastError();
   }
   static cudaError_t cfg = configure_merge();
   if (cfg != cudaSuccess) return cfg;
   constexpr int E = kMaxK / 32;
   const size_t smem = static_cast<size_t>(kMergeWarps) * 32 * E * (sizeof(int64_t) + sizeof(uint32_t));
-  xchg_merge_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(local_base, world, cap, s_bytes, k_in, k_out, out_scores, out_ids);
+  xchg_merge_kernel<E><<<batch, kMergeWarps * 32, smem, st>>>(local_base, world, cap, s_bytes, k_in, k_out, out_scores, out_ids,
+                                                                timeout_ns, err_word);
   return cudaGetLastError();
 }
 

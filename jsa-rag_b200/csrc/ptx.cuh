@@ -18,9 +18,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
@@ -40,12 +37,60 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+// Non-blocking probe of a barrier phase (one poll, never suspends).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.  Every wait of the scan
+// is on work of the same CTA (pair), so the bound is a wall-clock one far above any legitimate stall (SM preemption,
+// a debugger): 20 s measured with %globaltimer, looked at every 64k polls.
+constexpr uint64_t kMbarTimeoutNs = 20ull * 1000000000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 0xFFFFu) == 0u) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kMbarTimeoutNs) __trap();
+    }
   }
+}
+// Barriers that also collect arrivals of the other CTA of a pair are waited on the same way: what crosses the
+// pair is tensor-memory / async-proxy state ordered by the tcgen05 fences around the wait, no generic-proxy data,
+// so the default (CTA-scope) acquire is sufficient — a cluster-scope one would cost an L1 invalidation per poll.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+// ------------------------------------------------------------------ CTA pairs (clusters of 2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ named barriers
@@ -53,33 +98,6 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// bar.red.or: barrier among `nthreads` threads that also ORs a predicate across them
-__device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred pi, po;\n\t"
-      "setp.ne.u32 pi, %3, 0;\n\t"
-      "barrier.cta.red.or.pred po, %1, %2, pi;\n\t"
-      "selp.u32 %0, 1, 0, po;\n\t}"
-      : "=r"(out)
-      : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred))
-      : "memory");
-  return out != 0;
-}
-// Predicated shared-memory atomic add (inline PTX so the compiler neither warp-aggregates nor
-// serialises it against its neighbours); returns the old value, 0 when not executed.
-__device__ __forceinline__ int atoms_add_pred(uint32_t addr, int val, bool pred) {
-  int old;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %3, 0;\n\t"
-      "mov.u32 %0, 0;\n\t"
-      "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
-      : "=r"(old)
-      : "r"(addr), "r"(val), "r"(static_cast<uint32_t>(pred))
-      : "memory");
-  return old;
-}
 // One lane of the (converged) warp is elected; returns true on that lane only.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -117,6 +135,18 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t bar, uint
       : "memory");
 }
 
+// Same for a CTA pair (cta_group::2): the data lands in the executing CTA's shared memory, the completion
+// bytes are counted on an mbarrier of the pair's leader CTA (`bar_cluster` is a shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(const void* tmap, uint32_t bar_cluster, uint32_t dst_smem, int32_t c0,
+                                                 int32_t c1, uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(cache_hint)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
@@ -128,34 +158,35 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// Pair forms: the same warp of BOTH CTAs of the pair executes them.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers fp16 and bf16 operands with fp32 accumulation.
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same with the A operand read from tensor memory (TS form): a_tmem addresses 128 lanes x 8 columns
-// of packed 16-bit values (K = 16) — the query block never leaves TMEM.
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A * B, kind::f16 (fp16 and bf16 operands, fp32 accumulation); A from tensor memory (TS: a_tmem
+// addresses 128 lanes x 8 columns of packed 16-bit values per K = 16 step) or shared memory (SS), B from shared memory.
+// CTA-pair MMAs (cta_group::2, issued by the leader CTA only): M = 256 — rows [0,128) are the leader's A operand and
+// accumulator lanes, rows [128,256) the peer's; the B operand's N rows are split, the first N/2 in the leader's
+// shared memory and the second N/2 in the peer's, at the same offsets (one descriptor serves both).
+// Arrive on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair once all previously issued
+// tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -193,13 +224,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// One fp32 column for the warp's 32 lanes; the column is a runtime value.
-__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
-}
-
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (tile rows are 128 B = 64
 // 16-bit elements wide, 8-row groups are 1024 B apart).  Bit layout: start>>4 [0,14),
@@ -214,6 +238,85 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same descriptor as two 32-bit words: only the low word (start address) changes from MMA to MMA, so the issue
+// loop does 32-bit adds on it (the address field cannot carry out: shared memory is < 256 KiB).
+constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+
+// One K chunk (64 elements = four K=16 MMAs) in ONE asm block: the operand addresses of the four instructions are
+// derived inside the block (tensor-memory A: +8 columns per step; descriptor low words: +kBStep / +2), so the compiler
+// keeps them next to their MMA instead of hoisting dozens of them into (spilling) uniform registers.
+template <bool kPair, uint32_t kBStep>
+__device__ __forceinline__ void umma_ts_x4(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc_first) {
+  if (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 d0, d1, d2, d3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 d0, {%2, %5};\n\t"
+        "add.u32 b1, %2, %6;\n\tadd.u32 b2, b1, %6;\n\tadd.u32 b3, b2, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "mov.b64 d1, {b1, %5};\n\tmov.b64 d2, {b2, %5};\n\tmov.b64 d3, {b3, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], d0, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a1], d1, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], d2, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], d3, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, 1;\n\t}"
+        :
+        : "r"(tmem_d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kSw128DescHi), "n"(kBStep), "r"(0u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 d0, d1, d2, d3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 d0, {%2, %5};\n\t"
+        "add.u32 b1, %2, %6;\n\tadd.u32 b2, b1, %6;\n\tadd.u32 b3, b2, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "mov.b64 d1, {b1, %5};\n\tmov.b64 d2, {b2, %5};\n\tmov.b64 d3, {b3, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d0, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], d1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], d2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], d3, %3, 1;\n\t}"
+        :
+        : "r"(tmem_d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kSw128DescHi), "n"(kBStep)
+        : "memory");
+  }
+}
+template <bool kPair, uint32_t kBStep>
+__device__ __forceinline__ void umma_ss_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc_first) {
+  if (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 d0, d1, d2, d3, e0, e1, e2, e3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 d0, {%2, %5};\n\tmov.b64 e0, {%1, %5};\n\t"
+        "add.u32 b1, %2, %6;\n\tadd.u32 b2, b1, %6;\n\tadd.u32 b3, b2, %6;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 a2, %1, 4;\n\tadd.u32 a3, %1, 6;\n\t"
+        "mov.b64 d1, {b1, %5};\n\tmov.b64 d2, {b2, %5};\n\tmov.b64 d3, {b3, %5};\n\t"
+        "mov.b64 e1, {a1, %5};\n\tmov.b64 e2, {a2, %5};\n\tmov.b64 e3, {a3, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], e0, d0, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], e1, d1, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], e2, d2, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], e3, d3, %3, {%7, %7, %7, %7, %7, %7, %7, %7}, 1;\n\t}"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kSw128DescHi), "n"(kBStep), "r"(0u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 d0, d1, d2, d3, e0, e1, e2, e3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 d0, {%2, %5};\n\tmov.b64 e0, {%1, %5};\n\t"
+        "add.u32 b1, %2, %6;\n\tadd.u32 b2, b1, %6;\n\tadd.u32 b3, b2, %6;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 a2, %1, 4;\n\tadd.u32 a3, %1, 6;\n\t"
+        "mov.b64 d1, {b1, %5};\n\tmov.b64 d2, {b2, %5};\n\tmov.b64 d3, {b3, %5};\n\t"
+        "mov.b64 e1, {a1, %5};\n\tmov.b64 e2, {a2, %5};\n\tmov.b64 e3, {a3, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], e0, d0, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], e1, d1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], e2, d2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], e3, d3, %3, 1;\n\t}"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kSw128DescHi), "n"(kBStep)
+        : "memory");
+  }
+}
+
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major.
 // c_format [4,6)=1 (F32); a_format [7,10), b_format [10,13): 0 = F16, 1 = BF16;
 // n_dim [17,23) = N>>3; m_dim [24,29) = M>>4.

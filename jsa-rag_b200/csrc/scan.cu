@@ -208,9 +208,17 @@ constexpr int kSeedReaderSpins = 4096;   // ~0.6 ms: how long a thread waits for
 // ------------------------------------------------------------------------------------------------
 // The scan kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads, 1)
-mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_q,
-                 const ScanParams p) {
+// kPair = false: one CTA per SM works alone (UMMA M = 64 / 128, cta_group::1).
+// kPair = true : the two CTAs of a cluster (one TPC) form a tcgen05 CTA pair for 256 queries (UMMA M = 256,
+//   cta_group::2).  Each CTA keeps its own 128 queries in its own tensor memory and gets its own 128 x 64
+//   accumulator, but TMA-loads only HALF of every passage tile (32 of the 64 rows); the pair's MMAs, issued by the
+//   leader CTA, read both halves.  Per SM that is half the shared-memory fill per unit of tensor work — the limiter
+//   of the single-CTA kernel for batches >= 256 (one SM's TMA ingest, ~46 B/clk, against 96 KB per 1536 tensor
+//   cycles).  Barriers: full[] lives in the leader (one arrival per CTA + both CTAs' TMA bytes), empty[] / tfull[]
+//   are signalled in both CTAs by multicast tcgen05.commit, tempty[] / qready live in the leader and collect the
+//   epilogue warps of both CTAs.
+template <bool kPair, bool kBMn>
+__device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -221,12 +229,16 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   const int nk_ss = nk - nk_ts;                               // ... and in shared memory (dim > 768)
   const int S = p.num_stages;
   const int cps = p.chunks_per_stage;                            // K chunks one pipeline stage carries
-  const int stage_bytes = cps * kChunkBytes;
+  constexpr int kBoxRows = kPair ? kTileN / 2 : kTileN;          // passage rows this CTA loads per tile
+  constexpr int kBoxBytes = kBoxRows * kKChunk * 2;              // one K chunk of them (SWIZZLE_128B)
+  const int stage_bytes = cps * kBoxBytes;
+  const uint32_t cta_rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
   const int stages_per_tile = (nk + cps - 1) / cps;
   const uint32_t q_smem = base;                               // nk_ss chunks of [128 q x 64 el]
   const uint32_t st_smem = base + nk_ss * kQChunkBytes;       // S stages of 2 x [64 p x 64 el]
   uint8_t* ctrl = smem + nk_ss * kQChunkBytes + S * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);         // full[12] empty[12] tfull[2] tempty[2] qfull
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);         // full[12] empty[12] tfull[2] tempty[2] qfull qready
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 32);
 
   const uint32_t bar_full = ptx::smem_u32(bars);
@@ -234,6 +246,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t bar_qfull = bar_tempty + 16;
+  const uint32_t bar_qready = bar_qfull + 8;                  // pair mode: both CTAs' queries are in tensor memory
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,22 +256,23 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     ptx::prefetch_tensormap(&tmap_e);
     if (nk_ss > 0) ptx::prefetch_tensormap(&tmap_q);
     for (int s = 0; s < kMaxStages; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_full + 8 * s, kPair ? 2 : 1);   // pair: one arrival per CTA (the leader's carries the bytes)
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_tfull + 8 * b, 1);
-      ptx::mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+      ptx::mbar_init(bar_tempty + 8 * b, kPair ? 8 : 4);  // one arrival per epilogue warp (of both CTAs)
     }
-    ptx::mbar_init(bar_qfull, 1);
+    ptx::mbar_init(bar_qfull, kPair ? 2 : 1);
+    ptx::mbar_init(bar_qready, 8);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_s), kTmemCols);
-    ptx::tmem_relinquish();
+    if (kPair) { ptx::tmem_alloc_pair(ptx::smem_u32(tmem_ptr_s), kTmemCols); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_s), kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised too
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   // Programmatic dependent launch: let the next kernel of the stream begin its own prologue now.  Up to
@@ -295,10 +309,17 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     // =========================== TMA producer ===========================
     if (nk_ss > 0) ptx::griddep_wait();   // the K tail is read from the prepared-query buffer
     if (nk_ss > 0 && ptx::elect_one()) {  // K tail of the queries: resident in shared memory
-      ptx::mbar_arrive_expect_tx(bar_qfull, nk_ss * kQChunkBytes);
-      for (int kc = 0; kc < nk_ss; ++kc)
-        ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, (nk_ts + kc) * kKChunk, q_row0,
-                         ptx::kEvictLast);
+      if (kPair) {
+        const uint32_t qf = ptx::mapa(bar_qfull, 0);
+        if (leader) ptx::mbar_arrive_expect_tx(bar_qfull, 2 * nk_ss * kQChunkBytes); else ptx::mbar_arrive_cluster(qf);
+        for (int kc = 0; kc < nk_ss; ++kc)
+          ptx::tma_load_2d_pair(&tmap_q, qf, q_smem + kc * kQChunkBytes, (nk_ts + kc) * kKChunk, q_row0, ptx::kEvictLast);
+      } else {
+        ptx::mbar_arrive_expect_tx(bar_qfull, nk_ss * kQChunkBytes);
+        for (int kc = 0; kc < nk_ss; ++kc)
+          ptx::tma_load_2d(&tmap_q, bar_qfull, q_smem + kc * kQChunkBytes, (nk_ts + kc) * kKChunk, q_row0,
+                           ptx::kEvictLast);
+      }
     }
     __syncwarp();
     int stage = 0;
@@ -309,15 +330,31 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
         const long long w0 = want_stats ? clock64() : 0;
         ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
         if (want_stats) st_a += clock64() - w0;
-        if (ptx::elect_one()) {
+        if ((p.flags & kDbgNoTma) != 0) {
+          if (ptx::elect_one()) {
+            if (!kPair || leader) ptx::mbar_arrive(bar_full + 8 * stage);
+            else ptx::mbar_arrive_cluster(ptx::mapa(bar_full + 8 * stage, 0));
+          }
+        } else if (ptx::elect_one()) {
           const int kc0 = si * cps;
           const int nch = nk - kc0 < cps ? nk - kc0 : cps;
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, nch * kChunkBytes);
-          for (int c = 0; c < nch; ++c) {
-            // tensor-map coordinates are (inner, outer): (dim, passage) for [n, dim], (passage, dim) for [dim, n]
-            const int c_dim = (kc0 + c) * kKChunk, c_row = t * kTileN;
-            ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * stage_bytes + c * kChunkBytes,
-                             p.b_mn ? c_row : c_dim, p.b_mn ? c_dim : c_row, stream_hint);
+          if (kPair) {
+            // this CTA's half of the tile; the bytes of both halves are counted on the leader's barrier
+            const uint32_t full = ptx::mapa(bar_full + 8 * stage, 0);
+            if (leader) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * nch * kBoxBytes);
+            else ptx::mbar_arrive_cluster(full);
+            const int c_row = t * kTileN + static_cast<int>(cta_rank) * kBoxRows;
+            for (int c = 0; c < nch; ++c)
+              ptx::tma_load_2d_pair(&tmap_e, full, st_smem + stage * stage_bytes + c * kBoxBytes, (kc0 + c) * kKChunk, c_row,
+                                    stream_hint);
+          } else {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, nch * kBoxBytes);
+            for (int c = 0; c < nch; ++c) {
+              // tensor-map coordinates are (inner, outer): (dim, passage) for [n, dim], (passage, dim) for [dim, n]
+              const int c_dim = (kc0 + c) * kKChunk, c_row = t * kTileN;
+              ptx::tma_load_2d(&tmap_e, bar_full + 8 * stage, st_smem + stage * stage_bytes + c * kBoxBytes,
+                               kBMn ? c_row : c_dim, kBMn ? c_dim : c_row, stream_hint);
+            }
           }
         }
         __syncwarp();
@@ -326,63 +363,87 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     }
     if (want_stats && lane == 0) my_stats[kStProdWait] = st_a;
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (nk_ss > 0) ptx::mbar_wait(bar_qfull, 0);
-    ptx::named_bar_sync(2, 160);  // the epilogue warps have written the queries to TMEM
+   if (!kPair || leader) {
+    // =========================== MMA issuer (pair: the leader CTA's only) ===========================
+    if (nk_ss > 0) { if (kPair) ptx::mbar_wait_cluster(bar_qfull, 0); else ptx::mbar_wait(bar_qfull, 0); }
+    // the epilogue warps (of both CTAs) have written the queries to TMEM
+    if (kPair) ptx::mbar_wait_cluster(bar_qready, 0); else ptx::named_bar_sync(2, 160);
     ptx::tc_fence_after();
-    int stage = 0;
+    const bool no_mma = !kPair && (p.flags & kDbgNoMma) != 0;
+    const uint32_t idesc = p.idesc;
+    // B: [rows x 64 el] boxes, SWIZZLE_128B.  K-major ([n, dim] index): rows are passages, a K=16 step advances 32 B
+    // inside the swizzle row (+2 in the 16-byte-granular address field).  MN-major ([dim, n] index): rows are dims,
+    // a K=16 step advances 16 rows = 2048 B (+128).
+    constexpr uint32_t kBStep = kBMn ? 128u : 2u;
+    // The MMAs of chunks [c0, c1) of one pipeline stage.  tcgen05.mma of this shape retires in 32 tensor cycles, so
+    // the issue loop itself has to stay well below that per MMA: one asm block per K chunk (4 MMAs) whose operand
+    // addresses are 32-bit adds inside the block, nothing branched on in between.
+    auto issue = [&](int c0, int c1, int kc0, uint32_t b_lo0, uint32_t d_tmem) {
+      int kc = kc0 + c0;
+      uint32_t b_lo = b_lo0 + static_cast<uint32_t>(c0) * (kBoxBytes >> 4);
+      uint32_t a_tmem = tmem_base + kc * (kKChunk / 2);             // A from TMEM: 8 columns per K=16 step
+      const int kc_end = kc0 + c1, ts_end = kc_end < nk_ts ? kc_end : nk_ts;
+#pragma unroll 1
+      for (; kc < ts_end; ++kc, b_lo += kBoxBytes >> 4, a_tmem += kKChunk / 2)
+        ptx::umma_ts_x4<kPair, kBStep>(d_tmem, a_tmem, b_lo, idesc, kc != 0 ? 1u : 0u);
+      uint32_t a_lo = ptx::sw128_desc_lo(q_smem + (kc - nk_ts) * kQChunkBytes);   // K tail: A from shared memory
+#pragma unroll 1
+      for (; kc < kc_end; ++kc, b_lo += kBoxBytes >> 4, a_lo += kQChunkBytes >> 4)
+        ptx::umma_ss_x4<kPair, kBStep>(d_tmem, a_lo, b_lo, idesc, kc != 0 ? 1u : 0u);
+    };
+    // A step = one pipeline stage.  What a step needs: its stage filled and, on a tile's first stage, the accumulator
+    // buffer drained.  The next step's barriers are probed (non-blocking) before the current step's last chunk is
+    // issued, so that in the steady state the hand-off costs the issuer nothing while MMAs are still queued.
+    const int n_steps = n_iter * stages_per_tile;
+    int stage = 0, si = 0, it = 0;
     uint32_t phase = 0;
-    int it = 0;
-    const bool no_mma = (p.flags & kDbgNoMma) != 0;
-    for (; it < n_iter; ++it) {
+    bool ready = false;
+    for (int s = 0; s < n_steps; ++s) {
       const int buf = it & 1;
-      long long w0 = want_stats ? clock64() : 0;
-      ptx::mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
-      if (want_stats) st_b += clock64() - w0;
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kTileN;
-      for (int si = 0; si < stages_per_tile; ++si) {
-        w0 = want_stats ? clock64() : 0;
+      if (!ready) {
+        if (si == 0) {
+          const long long w0 = want_stats ? clock64() : 0;
+          ptx::mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1u);
+          if (want_stats) st_b += clock64() - w0;
+        }
+        const long long w0 = want_stats ? clock64() : 0;
         ptx::mbar_wait(bar_full + 8 * stage, phase);
         if (want_stats) st_a += clock64() - w0;
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const bool last = si == stages_per_tile - 1;
-          if (no_mma) {
-            ptx::mbar_arrive(bar_empty + 8 * stage);
-            if (last) ptx::mbar_arrive(bar_tfull + 8 * buf);
-          } else {
-            const int kc0 = si * cps;
-            const int nch = nk - kc0 < cps ? nk - kc0 : cps;
-            for (int c = 0; c < nch; ++c) {
-              const int kc = kc0 + c;
-              // B: 64 passages x 64 el, SWIZZLE_128B.  K-major ([n, dim] index): rows are passages, a K=16
-              // step advances 32 B inside the swizzle row (+2 in the 16-byte-granular address field).
-              // MN-major ([dim, n] index): rows are dims, a K=16 step advances 16 rows = 2048 B (+128).
-              const uint64_t db = ptx::make_kmajor_sw128_desc(st_smem + stage * stage_bytes + c * kChunkBytes);
-              const uint32_t bstep = p.b_mn ? 128u : 2u;
-              if (kc < nk_ts) {
-                // A from TMEM: 8 columns (16 packed 16-bit values per lane) per K=16 step
-                const uint32_t a_tmem = tmem_base + kc * (kKChunk / 2);
-#pragma unroll
-                for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
-                  ptx::umma_f16_ts(d_tmem, a_tmem + 8 * k4, db + bstep * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
-              } else {
-                const uint64_t da = ptx::make_kmajor_sw128_desc(q_smem + (kc - nk_ts) * kQChunkBytes);
-#pragma unroll
-                for (int k4 = 0; k4 < kKChunk / kUmmaK; ++k4)
-                  ptx::umma_f16(d_tmem, da + 2 * k4, db + bstep * k4, p.idesc, (kc | k4) != 0 ? 1u : 0u);
-              }
-            }
-            ptx::umma_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs retire
-            if (last) ptx::umma_commit(bar_tfull + 8 * buf);
-          }
-        }
-        __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + kAccCol0 + buf * kTileN;
+      const bool last = si == stages_per_tile - 1;
+      const int kc0 = si * cps;
+      const int nch = nk - kc0 < cps ? nk - kc0 : cps;
+      const uint32_t b_lo0 = ptx::sw128_desc_lo(st_smem + stage * stage_bytes);
+      int nstage = stage + 1, nsi = si + 1, nit = it;
+      uint32_t nphase = phase;
+      if (nstage == S) { nstage = 0; nphase ^= 1u; }
+      if (nsi == stages_per_tile) { nsi = 0; ++nit; }
+      if (!no_mma && ptx::elect_one()) issue(0, nch - 1, kc0, b_lo0, d_tmem);
+      __syncwarp();
+      ready = false;
+      if (s + 1 < n_steps) {
+        ready = ptx::mbar_test_wait(bar_full + 8 * nstage, nphase);
+        if (nsi == 0) ready = ready && ptx::mbar_test_wait(bar_tempty + 8 * (nit & 1), ((nit >> 1) & 1) ^ 1u);
+        ready = __all_sync(0xffffffffu, ready);
+      }
+      if (ptx::elect_one()) {
+        if (no_mma) {
+          ptx::mbar_arrive(bar_empty + 8 * stage);
+          if (last) ptx::mbar_arrive(bar_tfull + 8 * buf);
+        } else {
+          issue(nch - 1, nch, kc0, b_lo0, d_tmem);
+          // stage reusable (in both CTAs of a pair) once these MMAs retire
+          if (kPair) ptx::umma_commit_pair(bar_empty + 8 * stage); else ptx::umma_commit(bar_empty + 8 * stage);
+          if (last) { if (kPair) ptx::umma_commit_pair(bar_tfull + 8 * buf); else ptx::umma_commit(bar_tfull + 8 * buf); }
+        }
+      }
+      __syncwarp();
+      stage = nstage; phase = nphase; si = nsi; it = nit;
     }
     if (want_stats && lane == 0) { my_stats[kStMmaWaitFull] = st_a; my_stats[kStMmaWaitTmem] = st_b; }
+   }
   } else {
     // =========================== epilogue / select ===========================
     // UMMA M=128: query m sits in TMEM lane m.  UMMA M=64 (passes of <= 64 queries; half the tensor
@@ -425,8 +486,15 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::named_bar_sync(2, 160);
+      if (kPair) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_qready, 0));
+      } else {
+        ptx::named_bar_sync(2, 160);
+      }
     }
+    // where this warp reports a drained accumulator buffer: the MMA issuer's CTA
+    const uint32_t tempty_at = kPair ? ptx::mapa(bar_tempty, 0) : bar_tempty;
 
     // ---- per-query state lives in registers ----
     // initial threshold: the k-th best score of the sampled pre-pass when there is one (a valid
@@ -448,7 +516,7 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+        if (lane == 0) { if (kPair) ptx::mbar_arrive_cluster(tempty_at + 8 * buf); else ptx::mbar_arrive(bar_tempty + 8 * buf); }
         uint32_t pm0 = 0, pm1 = 0;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
@@ -547,7 +615,9 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);  // the 64 scores are in registers now
+      if (lane == 0) {   // the 64 scores are in registers now
+        if (kPair) ptx::mbar_arrive_cluster(tempty_at + 8 * buf); else ptx::mbar_arrive(bar_tempty + 8 * buf);
+      }
       if (want_stats) { const long long w1 = clock64(); st_d += w1 - w0; w0 = w1; }
       if (no_select) continue;
 
@@ -643,21 +713,84 @@ mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   // ---------------- teardown ----------------
   if (want_stats && threadIdx.x == 0) my_stats[kStTotal] = clock64() - t_start;
   ptx::tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may exit (or free tensor memory) while the other can still signal its barriers
+  if (kPair) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) ptx::tmem_dealloc_pair(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-cudaError_t configure_scan(size_t smem_bytes) {
-  return cudaFuncSetAttribute(mips_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(smem_bytes));
+__global__ void __launch_bounds__(kScanThreads, 1)
+mips_scan_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_q,
+                 const ScanParams p) {
+  scan_body<false, false>(tmap_e, tmap_q, p);
+}
+
+// Index stored [dim, n_local] (the reference's own layout): the B operand is MN-major.
+__global__ void __launch_bounds__(kScanThreads, 1)
+mips_scan_dn_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_q,
+                    const ScanParams p) {
+  scan_body<false, true>(tmap_e, tmap_q, p);
+}
+
+// CTA-pair variant: launched with cluster dimension 2 (see launch_scan_pair).
+__global__ void __launch_bounds__(kScanThreads, 1)
+mips_scan_pair_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_q,
+                      const ScanParams p) {
+  scan_body<true, false>(tmap_e, tmap_q, p);
+}
+
+// The attribute is per function and device, not per handle: always the maximum, so that handles of different
+// dims on one GPU cannot lower each other's limit.
+cudaError_t configure_scan() {
+  cudaError_t e = cudaFuncSetAttribute(mips_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(mips_scan_dn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(mips_scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 
 cudaError_t launch_scan(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
                         size_t smem_bytes, cudaStream_t st) {
+  if (p.b_mn)
+    return launch_pdl(mips_scan_dn_kernel, dim3(grid), dim3(kScanThreads), smem_bytes, st, g_use_pdl, tmap_e, tmap_q, p);
   return launch_pdl(mips_scan_kernel, dim3(grid), dim3(kScanThreads), smem_bytes, st, g_use_pdl, tmap_e, tmap_q, p);
+}
+
+static void pair_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, size_t smem_bytes,
+                               cudaStream_t st) {
+  cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kScanThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+}
+
+// grid must be even: CTAs 2c and 2c+1 form pair c.
+cudaError_t launch_scan_pair(const CUtensorMap& tmap_e, const CUtensorMap& tmap_q, const ScanParams& p, int grid,
+                             size_t smem_bytes, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  pair_launch_config(cfg, attr, grid, smem_bytes, st);
+  return cudaLaunchKernelEx(&cfg, mips_scan_pair_kernel, tmap_e, tmap_q, p);
+}
+
+// How many CTA pairs the device keeps resident at once with this much shared memory (74 on a full B200).
+cudaError_t max_resident_pairs(size_t smem_bytes, int* out) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  pair_launch_config(cfg, attr, 2, smem_bytes, nullptr);
+  cfg.numAttrs = 1;
+  return cudaOccupancyMaxActiveClusters(out, mips_scan_pair_kernel, &cfg);
 }
 
 // ------------------------------------------------------------------------------------------------

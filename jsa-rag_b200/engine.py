@@ -124,7 +124,7 @@ class MipsEngine:
 
     # ------------------------------------------------------------------ diagnostics
     STAT_NAMES = ["prod_wait", "mma_wait_full", "mma_wait_tmem", "epi_wait_tmem", "epi_select", "epi_compact",
-                  "n_compact", "n_append", "total_cycles", "epi_ld", "epi_bar"]
+                  "n_compact", "n_append", "total_cycles", "epi_ld"]
 
     def debug_config(self, flags: int = 0, collect_stats: bool = False):
         """flags: 1 = skip select, 2 = skip MMAs (results meaningless).  Returns the stats tensor

@@ -85,6 +85,15 @@ int mips_bind_index_layout(mips_handle* h, const void* emb, int64_t n_local, int
 int mips_workspace_bytes(const mips_handle* h, int max_batch, int max_k, size_t* out);
 
 /*
+ * Lifetime of the INTERNAL workspace (used when `workspace` is NULL): it grows to the largest (batch, k) seen.  A
+ * captured CUDA graph of a search holds raw pointers into it, so the owner of such a graph calls
+ * mips_workspace_pin(h, +1) before capture and mips_workspace_pin(h, -1) after destroying the graph: while the pin
+ * count is positive an outgrown workspace is retired (kept allocated) instead of freed, and freed when the count
+ * returns to zero.
+ */
+int mips_workspace_pin(mips_handle* h, int delta);
+
+/*
  * Exact top-k inner-product search of `batch` queries over the bound shard.
  *   queries    device pointer, [batch, dim] row-major with row stride q_ld elements, q_dtype
  *              F32 / F16 / BF16; cast to the index dtype exactly like `allqueries.half()`

@@ -28,6 +28,7 @@ SYMBOLS = {
     "mips_bind_index": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64]),
     "mips_bind_index_layout": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64]),
     "mips_workspace_bytes": (c_int, [c_void_p, c_int, c_int, POINTER(c_size_t)]),
+    "mips_workspace_pin": (c_int, [c_void_p, c_int]),
     "mips_search_local": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "mips_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

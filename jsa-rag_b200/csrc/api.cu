@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 using namespace mips;
 
@@ -35,6 +36,8 @@ struct mips_handle {
   // internal buffers
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  int ws_pins = 0;                 // captured graphs holding pointers into ws (mips_workspace_pin)
+  std::vector<void*> ws_retired;   // outgrown while pinned: freed when the last pin goes
   void* sync = nullptr;  // zero-initialised: search token | per-CTA sample flags | tagged seeds (in-kernel sampled seeding)
   void* io = nullptr;  // device staging for mips_search_host: queries | scores | ids
   size_t io_bytes = 0;
@@ -236,6 +239,7 @@ void mips_destroy(mips_handle* h) {
   DeviceGuard g(h->device);
   if (h->sync) cudaFree(h->sync);
   if (h->ws) cudaFree(h->ws);
+  for (void* p : h->ws_retired) cudaFree(p);
   if (h->io) cudaFree(h->io);
   if (h->timing_ready)
     for (int i = 0; i < mips_handle::kMaxTimed; ++i) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
@@ -284,6 +288,19 @@ int mips_workspace_bytes(const mips_handle* h, int max_batch, int max_k, size_t*
   return MIPS_OK;
 }
 
+int mips_workspace_pin(mips_handle* h, int delta) {
+  if (!h) return MIPS_EINVAL;
+  if (h->ws_pins + delta < 0) return fail(h, MIPS_EINVAL, "workspace pin count would become negative");
+  h->ws_pins += delta;
+  if (h->ws_pins == 0 && !h->ws_retired.empty()) {
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->ws_retired) cudaFree(p);
+    h->ws_retired.clear();
+  }
+  return MIPS_OK;
+}
+
 int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t q_ld, int batch, int k,
                       int normalize, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                       void* stream) {
@@ -309,8 +326,12 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   } else {
     if (h->ws_bytes < w.total) {
       // grow-only internal workspace (sized for the largest request seen); not on the steady-state path
-      CUDA_TRY(h, cudaStreamSynchronize(st));
-      if (h->ws) cudaFree(h->ws);
+      if (h->ws && h->ws_pins > 0) {
+        h->ws_retired.push_back(h->ws);   // a captured graph still points into it
+      } else {
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        if (h->ws) cudaFree(h->ws);
+      }
       h->ws = nullptr; h->ws_bytes = 0;
       CUDA_TRY(h, cudaMalloc(&h->ws, w.total));
       h->ws_bytes = w.total;

@@ -69,6 +69,11 @@ class MipsEngine:
                                                  int(id_base), int(id_stride)), self._h, "mips_bind_index")
         self._store = store  # keep alive: the extension only borrows the pointer
 
+    def pin_workspace(self, delta: int) -> None:
+        """+1 while a captured CUDA graph holds pointers into the internal workspace, -1 when it is released: a
+        pinned workspace that a larger search outgrows is kept alive (retired) instead of freed."""
+        N.check(self._lib.mips_workspace_pin(self._h, int(delta)), self._h, "mips_workspace_pin")
+
     @property
     def n_local(self) -> int:
         return 0 if self._store is None else int(self._store.shape[0])

@@ -17,9 +17,16 @@ import torch.distributed as dist
 from . import _native as N
 
 
+class PeerExchangeTimeout(RuntimeError):
+    """A peer's block did not arrive within the exchange timeout (JSA_MIPS_XCHG_TIMEOUT_S, default 30 minutes — the
+    order of a collective watchdog; the reference tolerates 100000 s, src/slurm.py:181).  Nothing trapped: the CUDA
+    context is intact, the step that timed out returned padding, and the exchange has to be rebuilt."""
+
+
 class PeerExchange:
     """Collective object: every rank constructs it with the same capacity, calls ``merge`` the same number of times
-    with the same (batch, k) and closes it together."""
+    with the same (batch, k) and closes it together.  A rank may be arbitrarily late (checkpointing, logging, a GC
+    pause): its peers' wait kernels simply keep polling until the timeout."""
 
     def __init__(self, device: torch.device, block_capacity: int):
         self._lib = N.load()
@@ -59,9 +66,24 @@ class PeerExchange:
         rc = self._lib.mips_xchg_merge(self._h, ctypes.c_void_p(local_block.data_ptr()), local_block.numel(), s_bytes, batch,
                                        k_in, k_out, ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
                                        ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        if rc != N.MIPS_OK:
-            raise RuntimeError("mips_xchg_merge: " + (self._lib.mips_xchg_last_error(self._h) or b"").decode())
+        self._check(rc, "mips_xchg_merge")
         return out_s, out_i
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc == N.MIPS_OK:
+            return
+        msg = f"{what}: " + (self._lib.mips_xchg_last_error(self._h) or b"").decode("utf-8", "replace")
+        if rc == N.MIPS_ETIMEOUT:
+            raise PeerExchangeTimeout(msg)
+        raise RuntimeError(msg)
+
+    def status(self) -> None:
+        """Raises PeerExchangeTimeout if a wait kernel of this exchange has given up (host-side read, no launch)."""
+        if self._h:
+            self._check(self._lib.mips_xchg_status(self._h), "mips_xchg_status")
+
+    def set_timeout(self, seconds: float) -> None:
+        self._check(self._lib.mips_xchg_set_timeout_ms(self._h, max(1, int(seconds * 1000))), "mips_xchg_set_timeout_ms")
 
     def gather(self, local: torch.Tensor) -> torch.Tensor:
         """All-gather of equally shaped contiguous tensors: returns [W, *local.shape] (rank order)."""
@@ -72,8 +94,7 @@ class PeerExchange:
         rc = self._lib.mips_xchg_gather(self._h, ctypes.c_void_p(local.data_ptr()), local.numel() * local.element_size(),
                                         ctypes.c_void_p(out.data_ptr()),
                                         ctypes.c_void_p(torch.cuda.current_stream(local.device).cuda_stream))
-        if rc != N.MIPS_OK:
-            raise RuntimeError("mips_xchg_gather: " + (self._lib.mips_xchg_last_error(self._h) or b"").decode())
+        self._check(rc, "mips_xchg_gather")
         return out
 
     def _free(self):

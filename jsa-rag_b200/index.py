@@ -92,6 +92,9 @@ class B200Index(object):
             raise ValueError("embeddings must be [dim, n]")
         value = value.to(device=self._storage_device(), dtype=self.dtype)
         self._store = value.contiguous().t() if self.layout == "dn" else value.t().contiguous()
+        # shard sizes and the global-id mapping follow the new matrix.  With more than one rank this is collective
+        # (every rank assigns its own shard, like init_embeddings / load_index).
+        self._set_sharding(self._sharding)
 
     def init_embeddings(self, passages, dim: Optional[int] = EMBEDDINGS_DIM):
         """src/index.py:50-54 — allocates zeroed storage; passages were round-robin sharded by
@@ -295,7 +298,12 @@ class B200Index(object):
             raise RuntimeError("the peer exchange must be sized before graph capture (run one eager search first)")
         from .exchange import make_peer_exchange
         if x is not None:
-            x.close()
+            if getattr(self, "_live_graphs", 0) > 0:
+                # a captured search still stores into / reads from this exchange on replay (on every rank): keep it
+                # mapped until the last graph is released, and serve the larger request from a new one
+                self._retired_xchg = getattr(self, "_retired_xchg", []) + [x]
+            else:
+                x.close()
         x = make_peer_exchange(device, max(block_bytes, getattr(self, "_xchg_min_bytes", 1 << 20)))
         if x is None:
             self._p2p_off = True
@@ -324,6 +332,12 @@ class B200Index(object):
         dev = self._store.device
         prev_equal = self.equal_batch
         self.equal_batch = True
+        # The graph bakes in raw pointers into the engine's workspace and the exchange buffers.  From here until
+        # release() neither may be freed: the engine retires (instead of freeing) a workspace it outgrows, and
+        # _peer_exchange keeps an outgrown exchange mapped (a larger eager search in between is therefore safe).
+        engine = self._get_engine()
+        engine.pin_workspace(+1)
+        self._live_graphs = getattr(self, "_live_graphs", 0) + 1
         static_q = torch.zeros(batch, int(self._store.shape[1]), dtype=query_dtype, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -345,9 +359,18 @@ class B200Index(object):
             return state["out"]
 
         def release():
+            """Collective when an exchange was outgrown meanwhile (its unmapping is a barrier)."""
+            if state["graph"] is None:
+                return
             state["graph"] = None
             state["out"] = None
             torch.cuda.synchronize(dev)
+            engine.pin_workspace(-1)
+            self._live_graphs -= 1
+            if self._live_graphs == 0:
+                for old in getattr(self, "_retired_xchg", []):
+                    old.close()
+                self._retired_xchg = []
 
         run.release = release
         return run

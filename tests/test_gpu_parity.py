@@ -407,15 +407,20 @@ def test_cuda_graph_replay_of_a_search(eng, dev):
 
 @pytest.mark.parametrize("n,b,k", [(150_000, 300, 100), (150_000, 512, 20), (64, 260, 10), (1_000_000, 1024, 100), (40_000, 129, 500)])
 def test_multi_block_launches_match_single_block(eng, dev, n, b, k):
-    """Batches > 128 scan 2 or 4 query blocks per launch (CTAs share each passage tile through the L2);
-    results must be bit-identical to one block per launch (debug flag 32) and agree with the oracle."""
+    """Batches > 128 run on tcgen05 CTA pairs (cta_group::2, UMMA M = 256: 1, 2 or 4 pair blocks per launch, each
+    CTA loading half of every passage tile); flag 128 = the round-1 path (2 or 4 single-CTA query blocks per launch
+    sharing tiles through the L2).  Both must be bit-identical to one block per launch (debug flag 32) and agree
+    with the oracle."""
     e, q = _synth(n, 768, b, 5 + b, dev)
     m = _engine(eng, e)
     s, i = m.search(q, k)
     m.debug_config(32, False)
     s1, i1 = m.search(q, k)
+    m.debug_config(128, False)
+    s2, i2 = m.search(q, k)
     m.debug_config(0, False)
     assert torch.equal(i, i1) and torch.equal(s, s1)
+    assert torch.equal(i2, i1) and torch.equal(s2, s1)
     rs, ri = _torch_ref(e, q, k)
     exact = (q.half().double() @ e.double().T).cpu().numpy()
     rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
@@ -529,15 +534,74 @@ def test_adversarial_row_order(eng, dev, k):
     assert int(i.min()) > n // 4          # the winners sit in the late, high-scoring part of the index
 
 
+@pytest.mark.parametrize("n,d,b,k,dtype", [
+    (90_000, 1024, 512, 100, torch.float16),     # K tail of the queries in shared memory (SS-mode pair MMAs)
+    (90_000, 64, 1500, 10, torch.bfloat16),      # one K chunk per stage, 4 + 2 pair blocks
+    (31, 768, 256, 31, torch.float16),           # fewer tiles than pairs
+    (200_001, 768, 257, 100, torch.bfloat16),    # second CTA pair almost empty
+    (120_000, 768, 640, 300, torch.float16),     # big-k lists on pairs
+    (700_000, 768, 1024, 16, torch.float16),     # 4 pair blocks, in-kernel seeding (18 lists x 4 >= 4 k)
+])
+def test_cta_pair_scan_matches_oracle(eng, dev, n, d, b, k, dtype):
+    e, q = _synth(n, d, b, 77 + b, dev, dtype)
+    m = _engine(eng, e, dtype)
+    s, i = m.search(q, k)
+    m.debug_config(32, False)
+    s1, i1 = m.search(q, k)
+    m.debug_config(0, False)
+    assert torch.equal(i, i1) and torch.equal(s, s1)
+    rs, ri = _torch_ref(e, q, k, dtype)
+    exact = (q.to(dtype).double() @ e.double().T).cpu().numpy()
+    rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)
+    assert rep["ok"], rep["errors"][:3]
+
+
+def test_graph_survives_a_larger_eager_search(eng, dev):
+    """A captured search holds raw pointers into the engine workspace.  A later, larger eager search on the same
+    index outgrows that workspace; it must be retired, not freed, until the graph is released."""
+    e, q = _synth(200_000, 768, 640, 23, dev)
+    idx = eng.B200Index()
+    idx._store = e
+    idx._set_sharding("round_robin")
+    run = idx.make_graphed_search(16, 10)
+    want_s, want_i = idx.search(q[:16], 10)
+    want_s, want_i = want_s.clone(), want_i.clone()
+    big_s, big_i = idx.search(q, 1000)                 # batch 640, k 1000: a much larger workspace
+    filler = [torch.full((1 << 22,), 7, dtype=torch.int64, device=dev) for _ in range(8)]   # would reuse freed memory
+    s1, i1 = run(q[:16])
+    torch.cuda.synchronize()
+    assert torch.equal(i1, want_i) and torch.equal(s1, want_s)
+    s2, i2 = idx.search(q, 1000)
+    assert torch.equal(i2, big_i) and torch.equal(s2, big_s)
+    run.release()
+    run.release()                                      # idempotent
+    s3, i3 = idx.search(q[:16], 10)
+    assert torch.equal(i3, want_i)
+    del filler
+
+
+def test_handles_of_different_dims_share_a_device(eng, dev):
+    """The dynamic shared-memory limit is a per-function attribute: a dim-768 handle created after a dim-1024 one
+    must not lower it."""
+    e1, q1 = _synth(20_000, 1024, 9, 3, dev)
+    m1 = _engine(eng, e1)
+    e2, q2 = _synth(20_000, 768, 9, 4, dev)
+    m2 = _engine(eng, e2)
+    for m, e, q in ((m1, e1, q1), (m2, e2, q2), (m1, e1, q1)):
+        s, i = m.search(q, 10)
+        rs, ri = _torch_ref(e, q, 10)
+        assert torch.equal(i, ri)
+
+
 def test_randomised_configurations(eng, dev):
     """Seeded random mix of shapes, dtypes, layouts, id mappings and k (interactions between the small /
     big-k modes, M=64 / M=128 / multi-block launches, the smem K tail of dim 1024 and both layouts)."""
     import random
     rnd = random.Random(20260718)
-    for trial in range(14):
+    for trial in range(20):
         d = rnd.choice([64, 256, 768, 768, 1024])
         n = rnd.choice([1, 63, 65, 1000, 9473, 40_000, 150_000, 300_001])
-        b = rnd.choice([1, 7, 64, 65, 128, 129, 300, 520])
+        b = rnd.choice([1, 7, 64, 65, 128, 129, 300, 520, 1100])
         k = min(n, rnd.choice([1, 10, 100, 128, 129, 400, 1024]))
         dtype = rnd.choice([torch.float16, torch.bfloat16])
         layout_dn = rnd.random() < 0.3

@@ -177,6 +177,16 @@ def test_load_passages_and_factory(eng, tmp_path):
         eng.load_or_initialize_index(Opt())
 
 
+def test_embeddings_setter_updates_the_sharding(eng):
+    """Direct assignment (which the setter supports) must refresh shard sizes and the global-id mapping."""
+    idx = eng.B200Index(device="cpu")
+    idx.is_in_gpu = False
+    idx.embeddings = torch.randn(768, 37)
+    assert idx._all_counts == [37] and (idx._id_base, idx._id_stride) == (0, 1)
+    idx.embeddings = torch.randn(768, 11)
+    assert idx._all_counts == [11]
+
+
 def test_candidate_packing_single_process(eng):
     s = torch.randn(3, 5)
     i = torch.randint(0, 1 << 40, (3, 5))

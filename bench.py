@@ -4,7 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
-A "step" is one search of a batch of 64 queries (top-100) over the whole 33M x 768 fp16 index.
+A "step" is one search of a batch of 64 queries (top-100) over the whole 33M x 768 fp16 index
+(--searches-per-step 2 = the JSA training step's posterior + prior searches back to back, src/rag.py:1804-1825).
 At N=1 the index lives on one B200 (BASELINE configs[1]); at N>1 it is row-sharded round-robin over
 the ranks (configs[2]), every rank contributes batch/N queries, and a step is the reference's
 distributed search_knn flow: query all-gather -> local fused scan+select -> ONE all-gather of
@@ -41,6 +42,10 @@ def parse_args():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--searches-per-step", type=int, default=1)
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-api-e2e", action="store_true")
     return ap.parse_args()
 
 
@@ -49,7 +54,7 @@ def workload(args, world):
             "rows": args.rows, "dim": args.dim, "batch": args.batch, "k": args.k,
             "sharding": "single shard" if world == 1 else f"round-robin rows over {world} ranks",
             "l2": "index pass (rows*dim*2 bytes per rank) exceeds the 126 MB L2; no flush needed",
-            "queries_per_rank": args.batch // world}
+            "queries_per_rank": args.batch // world, "searches_per_step": args.searches_per_step}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -80,10 +85,39 @@ def cpu_reference_rate(args, reps, warm=1):
         times.append(time.perf_counter() - t0)
     t = float(np.median(times))
     qps_full = args.batch / (t * args.rows / n_s)
+    # the reference's whole search_knn (doc_map lookups + list building, src/index.py:133-134,152-157) on the same
+    # sample: the arithmetic scales with the rows, the host tail (B*k lookups) does not
+    pool = [{"id": str(i), "title": f"title {i}", "text": f"passage text {i}"} for i in range(1 << 12)]
+    doc_map = _RefPool(pool, n_s)
+    sc, ix = O.cpu_search_arith(q, emb, args.k)
+    tails = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        O.search_knn_tail(sc, ix, doc_map, args.k)
+        tails.append(time.perf_counter() - t0)
+    tail = float(np.median(tails))
     return {"value": qps_full, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{n_s} of {args.rows} rows (fp16 [dim, n] layout), batch {args.batch}, top-{args.k}; "
                       f"median of {reps} passes, {t*1e3:.1f} ms each; scaled linearly to the full index",
-            "seconds_per_sample_pass": t}
+            "seconds_per_sample_pass": t,
+            "search_knn": {"value": args.batch / (t * args.rows / n_s + tail), "unit": UNIT,
+                           "host_tail_ms": tail * 1e3,
+                           "what": "reference search_knn incl. doc_map lookups and list building (src/index.py:123-158): "
+                                   "arithmetic scaled to the full index + the measured, size-independent host tail"}}
+
+
+class _RefPool:
+    """doc_map stand-in for timing: n keys that map onto a small pool of passage dicts (a 33M-entry dict of dicts would
+    take minutes and tens of GB to build; the lookups cost the same)."""
+
+    def __init__(self, pool, n):
+        self.pool, self.n = pool, n
+
+    def __getitem__(self, i):
+        return self.pool[i & (len(self.pool) - 1)]
+
+    def __len__(self):
+        return self.n
 
 
 def run_reference(args):
@@ -97,7 +131,7 @@ def run_reference(args):
             "dtype": "f16", "data": "synthetic", "impl": "reference", "config": workload(args, world),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "api_e2e": cb["search_knn"], "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -151,8 +185,121 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------
+class PooledDocMap:
+    """doc_map for the api_e2e leg: n_local keys -> references into a pool of 2^17 synthetic passage dicts.  The host
+    tail of search_knn (object gather, list building, score rounding) costs what it costs with distinct dicts; building
+    33M distinct dicts would add minutes and tens of GB to a benchmark that does not read their text."""
+
+    def __init__(self, n, pool_bits=17):
+        self.n = n
+        self.pool = [{"id": str(i), "title": f"title {i}", "text": f"synthetic passage {i}"} for i in range(1 << pool_bits)]
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self.pool[i & (len(self.pool) - 1)]
+
+    def as_object_array(self):
+        import numpy as np
+        tab = np.empty(len(self.pool), dtype=object)
+        tab[:] = self.pool
+        return tab[np.arange(self.n, dtype=np.int64) & (len(self.pool) - 1)]
+
+
+def parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets):
+    """Correctness evidence carried by the bench line (outside every timed region): the searches that were timed are
+    checked against planted nearest neighbours on the full index, against the NCCL all-gather + merge path bit for
+    bit (N > 1), and against the reference arithmetic (oracle, CPU) on a sub-shard with oracle.compare_topk."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import flat_index_oracle as O   # checker only
+
+    checked, ok, notes = [], True, {}
+    n_loc = int(index._store.shape[0])
+    per = q_sets[0].shape[0]
+    k = args.k
+
+    # ---- (1) planted nearest neighbours over the full index: query = own passage row + 2 % noise
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    rows = torch.randint(0, n_loc, (per,), generator=g, device=dev)
+    qp = index._store[rows].float()
+    qp = torch.nn.functional.normalize(qp + 0.02 * torch.randn(qp.shape, generator=g, device=dev) / (args.dim ** 0.5), dim=1)
+    s, i = index.search(qp, k)
+    want = index._id_base + rows * index._id_stride
+    planted_ok = bool((i[:, 0] == want).all()) and bool((s[:, 0] > 0.99).all()) and bool((s[:, 1:] <= s[:, :-1]).all())
+    checked.append("planted nearest neighbours (full index, every rank's queries)")
+    ok = ok and planted_ok
+
+    # ---- (2) peer-exchange path == NCCL all-gather + merge path, bit for bit
+    if world > 1:
+        ref_s, ref_i = index.search(q_sets[0], k)
+        ref_s, ref_i = ref_s.clone(), ref_i.clone()
+        saved = (getattr(index, "_xchg", None), getattr(index, "_xchg_q", None))
+        if saved[0]:
+            index._xchg, index._xchg_q = False, False
+            n_s, n_i = index.search(q_sets[0], k)
+            index._xchg, index._xchg_q = saved
+            same = torch.equal(n_s, ref_s) and torch.equal(n_i, ref_i)
+            checked.append("nvlink peer exchange == nccl all-gather + merge (bit-identical scores and ids)")
+            ok = ok and same
+        else:
+            notes["exchange"] = "nccl path only (no peer mapping): nothing to compare"
+
+    # ---- (3) oracle on a sub-shard: the first rows of every rank's shard form a small index with the same sharding
+    sub_total = int(min(2_000_000, max(100_000, (1 << 27) // max(1, args.batch))))
+    sub_n = max(k, min(n_loc, sub_total // world))
+    if world > 1:
+        t = torch.tensor([sub_n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        sub_n = int(t.item())
+    sub = eng.B200Index(dtype=tdtype)
+    sub._store = index._store[:sub_n]
+    sub._set_sharding("round_robin")
+    sub.equal_batch = True
+    ss, si = sub.search(q_sets[0], k)
+    if world > 1:
+        all_s = torch.empty((world,) + tuple(ss.shape), dtype=ss.dtype, device=dev)
+        all_i = torch.empty((world,) + tuple(si.shape), dtype=si.dtype, device=dev)
+        all_q = torch.empty((world,) + tuple(q_sets[0].shape), dtype=q_sets[0].dtype, device=dev)
+        all_e = torch.empty((world, sub_n, args.dim), dtype=tdtype, device=dev)
+        dist.all_gather_into_tensor(all_s, ss.contiguous())
+        dist.all_gather_into_tensor(all_i, si.contiguous())
+        dist.all_gather_into_tensor(all_q, q_sets[0].contiguous())
+        dist.all_gather_into_tensor(all_e, sub._store.contiguous())
+        ss, si, qq = all_s.flatten(0, 1), all_i.flatten(0, 1), all_q.flatten(0, 1)
+        emb = all_e.permute(1, 0, 2).reshape(sub_n * world, args.dim)     # global id = local * W + rank
+        sub.close_exchange()
+    else:
+        qq, emb = q_sets[0], sub._store
+    if rank == 0:
+        exact = (qq.to(tdtype).float() @ emb.float().T).cpu().numpy()      # exact products, fp32 accumulation
+        e_cpu = emb.cpu()
+        e_dn = e_cpu.t().contiguous() if tdtype == torch.bfloat16 else O.make_embeddings_dn(e_cpu)
+        torch.set_num_threads(os.cpu_count() or 1)
+        r_s, r_i = O.compute_scores_and_indices(qq.cpu(), e_dn, k)         # src/index.py:118-119 on the host
+        # north_star's tolerance (1e-3 relative) is stated against the reference's fp16 scores; the bf16 extension
+        # returns bf16-rounded scores (8-bit mantissa: half an ulp is 2^-8 = 3.9e-3 relative), hence 4e-3 there
+        rtol = 1e-3 if tdtype == torch.float16 else 4e-3
+        rep = O.compare_topk(si.cpu().numpy(), ss.cpu().numpy(), r_i.numpy(), r_s.float().numpy(), exact, rtol=rtol)
+        checked.append(f"oracle.compare_topk (rtol {rtol:g}) vs the reference arithmetic on a {sub_n * world}-row sub-index "
+                       f"({rep['id_set_equal_rows']}/{rep['rows']} rows with identical id sets, {rep['near_tie_diffs']} near-tie differences)")
+        ok = ok and rep["ok"]
+        if not rep["ok"]:
+            notes["oracle_errors"] = [str(e) for e in rep["errors"][:3]]
+    if world > 1:
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item() == 1.0)
+    out = {"checked": checked, "ok": ok}
+    out.update(notes)
+    return out
+
+
 def run_b200(args):
     import importlib
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -171,9 +318,10 @@ def run_b200(args):
 
     tdtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     n_loc = len(range(rank, args.rows, world))
+    sps = max(1, args.searches_per_step)
     # ---- synthetic shard: rows rank, rank+W, ... of the global index (src/index_io.py:41 sharding) ----
     index = eng.B200Index(dtype=tdtype)
-    index.init_embeddings([None] * 0, dim=args.dim)   # doc_map is not exercised by the tensor-level path
+    index.init_embeddings([None] * 0, dim=args.dim)   # doc_map is set for the api_e2e leg only
     index._store = torch.empty(n_loc, args.dim, dtype=tdtype, device=dev)
     index._set_sharding("round_robin")
     index.equal_batch = True   # every rank contributes batch/N queries
@@ -182,24 +330,36 @@ def run_b200(args):
         c = torch.randn(min(1 << 20, n_loc - a), args.dim, generator=g, device=dev)
         index._store[a:a + c.shape[0]] = torch.nn.functional.normalize(c, dim=1).to(tdtype)
     del c
-    q_all = torch.nn.functional.normalize(torch.randn(args.batch, args.dim, device=dev,
-                                                      generator=torch.Generator(device=dev).manual_seed(4321)), dim=1)
     per = args.batch // world
-    q_mine = q_all[rank * per:(rank + 1) * per].contiguous() if world > 1 else q_all
-    q_host = q_mine.cpu().pin_memory()
+    q_sets, q_hosts = [], []
+    for j in range(sps):     # one query set per search of a step (posterior / prior queries differ)
+        q_all = torch.nn.functional.normalize(torch.randn(args.batch, args.dim, device=dev,
+                                                          generator=torch.Generator(device=dev).manual_seed(4321 + j)), dim=1)
+        q_mine = q_all[rank * per:(rank + 1) * per].contiguous() if world > 1 else q_all
+        q_sets.append(q_mine)
+        q_hosts.append(q_mine.cpu().pin_memory())
 
     engine = index._get_engine()
     dbg = int(os.environ.get("JSA_MIPS_FLAGS", "0"))   # A/B switches of include/jsa_mips.h (0 = product path)
     engine.debug_config(8 | dbg, False)   # flag 8: CUDA events around every full-shard scan launch
 
     def step():
-        return index.search(q_mine, args.k)
+        for q in q_sets:
+            out = index.search(q, args.k)
+        return out
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def rank_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -214,53 +374,80 @@ def run_b200(args):
     t_wall0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        out = step()
+        step()
     ev1.record()
     sync_all()
     t_wall1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
+    ms = rank_max(ev0.elapsed_time(ev1))
     scan_ms = engine.scan_times_ms()
     p2p = bool(getattr(index, "_xchg", None))
     # own kernels per step: the local search + (push, wait+merge) with the peer exchange, or the merge after NCCL
     p2p_q = bool(getattr(index, "_xchg_q", None))
-    launches = engine.last_launch_count() + (((2 if p2p else 1) + (2 if p2p_q else 0)) if world > 1 else 0)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    launches = sps * (engine.last_launch_count() + (((2 if p2p else 1) + (2 if p2p_q else 0)) if world > 1 else 0))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
+    # ---- sustained load: the same step back to back for >= sustained_seconds (the timed region above is a burst
+    #      of a fraction of a second; a training loop sits at the 1 kW power cap) ----
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / max(1e-3, ms / args.steps)) + 1)
+        if world > 1:
+            t = torch.tensor([n_sus], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_sus = int(t.item())
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        sync_all()
+        engine.scan_times_ms()
+        w0 = time.perf_counter()
+        ev0.record()
+        for it in range(n_sus):
+            step()
+            if it % 64 == 63:
+                engine.scan_times_ms()          # keep only the tail of the run (at most 256 launches are recorded)
+        ev1.record()
+        sync_all()
+        w1 = time.perf_counter()
+        sus_ms = rank_max(ev0.elapsed_time(ev1))
+        sus_scan = engine.scan_times_ms()
+        sus_clocks = sampler2.stop(w0 + 0.5 * (w1 - w0), w1) if rank == 0 else None   # second half: settled clocks
+        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "value": args.batch * sps * n_sus / (sus_ms * 1e-3),
+                     "ms_per_step": sus_ms / n_sus, "avg_launch_ms": (sum(sus_scan) / len(sus_scan)) if sus_scan else None,
+                     "clocks": sus_clocks}
+
     # ---- end to end through the public API with HOST buffers (H2D of the queries + D2H of the result) ----
-    res_s = torch.empty(q_mine.shape[0], args.k, dtype=torch.float32).pin_memory()
-    res_i = torch.empty(q_mine.shape[0], args.k, dtype=torch.int64).pin_memory()
+    res_s = torch.empty(per if world > 1 else args.batch, args.k, dtype=torch.float32).pin_memory()
+    res_i = torch.empty(per if world > 1 else args.batch, args.k, dtype=torch.int64).pin_memory()
 
     graphed = None
     engine.debug_config(dbg, False)   # no event records inside the captured graph
     if world > 1:
         # a ~1 ms distributed search is sensitive to ~150 us of Python/launch overhead per step: replay a CUDA
         # graph of the same public search (collectives included); fall back to the eager call if capture fails
-        ok = torch.ones(1, device=dev)
+        okf = torch.ones(1, device=dev)
         try:
-            graphed = index.make_graphed_search(q_mine.shape[0], args.k)
+            graphed = index.make_graphed_search(per, args.k)
         except Exception as ex:  # noqa: BLE001
-            ok.zero_()
+            okf.zero_()
             sys.stderr.write(f"[rank {rank}] CUDA-graph capture unavailable, eager e2e path: {ex}\n")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() == 0:
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() == 0:
             if graphed is not None:
                 graphed.release()
             graphed = None
 
     def e2e_step():
-        if world == 1:
-            engine.search_host(q_host, args.k, out=(res_s, res_i))          # C ABI: mips_search_host
-        else:
-            if graphed is not None:
-                s, i = graphed(q_host)
+        for qh in q_hosts:
+            if world == 1:
+                engine.search_host(qh, args.k, out=(res_s, res_i))          # C ABI: mips_search_host
             else:
-                s, i = index.search(q_host.to(dev, non_blocking=True), args.k)
-            res_s.copy_(s, non_blocking=True); res_i.copy_(i, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+                if graphed is not None:
+                    s, i = graphed(qh)
+                else:
+                    s, i = index.search(qh.to(dev, non_blocking=True), args.k)
+                res_s.copy_(s, non_blocking=True); res_i.copy_(i, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
         e2e_step()
@@ -269,17 +456,41 @@ def run_b200(args):
     for _ in range(args.steps):
         e2e_step()
     sync_all()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = rank_max(time.perf_counter() - t0)
+    if graphed is not None:
+        graphed.release()          # graphs that captured NCCL kernels must die before the communicator
+        graphed = None
+
+    # ---- the reference-facing call itself: search_knn -> (docs, scores) as nested Python lists ----
+    api = None
+    if not args.no_api_e2e:
+        index.doc_map = PooledDocMap(n_loc)
+        q_dev = q_sets[0]
+        for _ in range(2):
+            index.search_knn(q_dev, args.k)
+        sync_all()
+        n_api = max(3, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(n_api):
+            docs, scores = index.search_knn(q_dev, args.k)
+        sync_all()
+        api_s = rank_max(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(n_api):
+            index.search(q_dev, args.k)
+        sync_all()
+        dev_s = rank_max(time.perf_counter() - t0)
+        assert len(docs) == q_dev.shape[0] and len(docs[0]) == args.k and isinstance(scores[0][0], float)
+        api = {"value": args.batch * n_api / api_s, "unit": UNIT, "ms_per_search": 1e3 * api_s / n_api,
+               "host_tail_ms": 1e3 * (api_s - dev_s) / n_api,
+               "what": "B200Index.search_knn (reference signature, src/index.py:123-158): device search + D2H + passage "
+                       "dicts for the k winners of this rank's queries + fp16-rounded score lists",
+               "passages": getattr(index, "last_passage_path", None)}
+
+    parity = None if args.no_parity else parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets)
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
         n_launch = max(1, len(scan_ms))
         scan_avg_ms = sum(scan_ms) / n_launch
@@ -287,8 +498,8 @@ def run_b200(args):
         if args.batch >= 256:
             # several query blocks per launch: the scan is tensor-core bound (BASELINE.md crossover B* ~ 215)
             bound, unit = "tensor", "TFLOP/s"
-            algo = 2.0 * args.batch * n_loc * args.dim / launches_per_step            # flops per launch (average)
-            achieved = algo / (scan_avg_ms * 1e-3) / 1e12 if scan_ms else None
+            per_launch = 2.0 * args.batch * sps * n_loc * args.dim / launches_per_step   # flops per launch (average)
+            scale = 1e12
             if "bf16_tflops_sustained" in peaks:
                 peak, peak_src = float(peaks["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
             else:
@@ -296,37 +507,55 @@ def run_b200(args):
             algo_key = "algorithmic_flops_per_launch"
         else:
             bound, unit = "hbm", "GB/s"
-            algo = float(n_loc * args.dim * 2)                                         # index bytes, read once per launch
-            achieved = algo / (scan_avg_ms * 1e-3) / 1e9 if scan_ms else None
+            per_launch = float(n_loc * args.dim * 2)                                      # index bytes, read once per launch
+            scale = 1e9
+            if "hbm_gbs" in peaks:
+                peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            else:
+                peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
             algo_key = "algorithmic_bytes_per_launch"
-        traffic = None
+        achieved = per_launch / (scan_avg_ms * 1e-3) / scale if scan_ms else None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and args.batch == 64 and args.rows == 33_000_000:
-            traffic = json.load(open(tpath)).get(f"n{world}")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            ent = tj.get("per_launch", {}).get(f"rows{n_loc}_dim{args.dim}_b{args.batch}_k{args.k}_{args.dtype}")
+            if ent:
+                traffic, traffic_src = ent["dram_bytes"], ent["source"]
+        roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "mips::mips_scan_pair_kernel (full-shard pass, CTA pairs)" if args.batch > 128 and not (dbg & (128 | 32))
+                          else "mips::mips_scan_kernel (full-shard pass)",
+                "peak_source": peak_src, algo_key: per_launch, "avg_launch_ms": scan_avg_ms,
+                "launches_timed": len(scan_ms), "launches_per_step": launches_per_step}
+        if sustained is not None:
+            sa = per_launch / (sustained["avg_launch_ms"] * 1e-3) / scale if sustained["avg_launch_ms"] else None
+            roof["sustained"] = {"achieved": sa, "frac": (sa / peak) if sa else None, "unit": unit,
+                                 "avg_launch_ms": sustained["avg_launch_ms"], "seconds": sustained["seconds"],
+                                 "steps": sustained["steps"], "value": sustained["value"], "value_unit": UNIT,
+                                 "sm_mhz": (sustained["clocks"] or {}).get("sm_mhz"),
+                                 "reasons": (sustained["clocks"] or {}).get("reasons")}
         line = {
-            "metric": METRIC, "value": args.batch * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": args.batch * sps * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
             "config": dict(workload(args, world), **({"exchange": "nvlink peer stores (queries and candidates) + wait-and-merge kernel" if p2p
                                                       else "nccl all-gather + merge kernel"} if world > 1 else {})),
-            "e2e": {"value": args.batch * args.steps / e2e_s, "unit": UNIT,
+            "e2e": {"value": args.batch * sps * args.steps / e2e_s, "unit": UNIT,
                     "path": "mips_search_host (C ABI, host buffers)" if world == 1 else
-                            ("B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)"
-                             if graphed is not None else "B200Index.search (public distributed API)"),
-                    "h2d_bytes_per_step": int(q_host.numel() * 4 * world),
-                    "d2h_bytes_per_step": int((res_s.numel() * 4 + res_i.numel() * 8) * world)},
+                            "B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)",
+                    "h2d_bytes_per_step": int(sum(q.numel() for q in q_hosts) * 4 * world),
+                    "d2h_bytes_per_step": int((res_s.numel() * 4 + res_i.numel() * 8) * world * sps)},
+            "api_e2e": api,
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "mips::mips_scan_kernel (full-shard pass)", "peak_source": peak_src,
-                         algo_key: algo, "avg_launch_ms": scan_avg_ms, "launches_timed": len(scan_ms),
-                         "launches_per_step": launches_per_step},
+            "roofline": roof,
+            "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             del index._store
             cb = cpu_reference_rate(args, reps=3)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "search_knn")}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -335,8 +564,6 @@ def run_b200(args):
         guard = threading.Timer(30.0, os._exit, (0,))
         guard.daemon = True
         guard.start()
-        if graphed is not None:
-            graphed.release()          # graphs that captured NCCL kernels must die before the communicator
         torch.cuda.synchronize()
         index.close_exchange()         # collective: peer-mapped exchange buffers are unmapped before anyone frees
         dist.barrier()

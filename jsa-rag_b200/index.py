@@ -63,6 +63,8 @@ class B200Index(object):
         # global id of local row r = id_base + r * id_stride  (see _set_sharding)
         self._id_base, self._id_stride = 0, 1
         self._sharding = "round_robin"
+        self._sharding_epoch = 0    # bumped by every (collective) _set_sharding: invalidates the shared passage store
+        self.last_passage_path = None
         self.round_scores_to_index_dtype = True  # reference returns fp16-rounded scores (src/index.py:118,153)
         # True: every rank always passes the same number of queries (fixed per-GPU batch, as in the
         # reference's training loop; evaluate.py:49-54 pads iterators to keep ranks in step) -> the size
@@ -111,6 +113,7 @@ class B200Index(object):
 
     def _set_sharding(self, mode: str) -> None:
         self._sharding = mode
+        self._sharding_epoch += 1
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
         n = 0 if self._store is None else int(self._store.shape[0])
         counts = dist_utils.all_gather_object(n) if w > 1 else [n]     # every rank knows every shard size
@@ -317,6 +320,9 @@ class B200Index(object):
             if x:
                 x.close()
             setattr(self, which, None)
+        if getattr(self, "_pstore", None) is not None:
+            self._pstore.close()
+            self._pstore, self._store_epoch = None, None
 
     def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
         """Captures one search for a fixed per-rank batch into a CUDA graph — on several ranks the whole
@@ -385,15 +391,33 @@ class B200Index(object):
         return owner, gids - starts[owner]
 
     def _resolve_docs(self, my_ids: torch.Tensor) -> List[List[dict]]:
-        """global ids [b,k] -> passage dicts.  Single rank: local lookup.  Multi rank: every rank knows
-        the merged winners of *all* queries (the merge is replicated), so each owner sends every rank
-        exactly the dicts that rank needs (an all-to-all of pickled objects: k winners per query, not the
-        W*k candidates the reference ships through 2*W gathers)."""
+        """global ids [b,k] -> passage dicts.  Rows of this rank's own shard come out of the in-memory table (one
+        vectorised gather instead of b*k dict lookups; the dict OBJECTS of ``doc_map``, like the reference).  Winners
+        owned by other ranks are read from the node-shared passage store (passages.py): no collective, no text over
+        NVLink.  Only when the ranks do not share a host is the winners' text exchanged through the process group
+        (one all-to-all: k winners per query, not the W*k candidates the reference ships through 2*W gathers)."""
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
         ids_np = my_ids.cpu().numpy()
         if w == 1:
             loc = (ids_np - self._id_base) // self._id_stride
-            return self._doc_table()[loc].tolist()      # one vectorised gather instead of b*k dict lookups
+            self.last_passage_path = "local table"
+            return self._doc_table()[loc].tolist()
+        store = self._shared_passages()
+        if store is not None:
+            self.last_passage_path = "local table + node-shared passage store (no collective)"
+            flat = ids_np.reshape(-1)
+            owner, local = self._owner_and_local(flat)
+            out = np.empty(flat.shape[0], dtype=object)
+            mine = owner == r
+            if mine.any():
+                out[mine] = self._doc_table()[local[mine]]
+            if (~mine).any():
+                fetched = store.get_many(owner[~mine], local[~mine])
+                tmp = np.empty(len(fetched), dtype=object)
+                tmp[:] = fetched
+                out[~mine] = tmp
+            return out.reshape(ids_np.shape).tolist()
+        self.last_passage_path = "all-to-all of the winners' pickled passages"
         all_ids, offs = self._last_all
         all_np = all_ids.cpu().numpy()
         owner, local = self._owner_and_local(all_np.reshape(-1))
@@ -410,14 +434,37 @@ class B200Index(object):
             merged.update(part)
         return [[merged[int(g)] for g in row] for row in ids_np]
 
+    def _shared_passages(self):
+        """The node-shared store of every rank's passages, (re)built collectively after the shard layout changed
+        (init_embeddings / load_index / assignment to .embeddings all pass through _set_sharding on every rank).
+        None: ranks on different hosts, JSA_MIPS_PASSAGES=a2a, or the store could not be written."""
+        if os.environ.get("JSA_MIPS_PASSAGES", "store").lower() == "a2a":
+            return None
+        if getattr(self, "_store_epoch", None) != self._sharding_epoch:
+            old = getattr(self, "_pstore", None)
+            if old is not None:
+                old.close()
+            from .passages import PassageStore
+            self._pstore = PassageStore.build_shared(self.doc_map, len(self.doc_map))
+            self._store_epoch = self._sharding_epoch
+        return self._pstore
+
+    def refresh_passages(self) -> None:
+        """Collective.  Call after mutating ``doc_map`` in place on a multi-rank index: the other ranks read this
+        rank's passages from the node-shared store, which is rebuilt at the next search_knn."""
+        self._sharding_epoch += 1
+
     def _doc_table(self) -> np.ndarray:
         """doc_map ({local row -> passage dict}, the reference's public attribute) as an object array,
         rebuilt only when the dict object or its size changes."""
         key = (id(self.doc_map), len(self.doc_map))
         if getattr(self, "_doc_table_key", None) != key:
-            tab = np.empty(len(self.doc_map), dtype=object)
-            for i in range(len(self.doc_map)):
-                tab[i] = self.doc_map[i]
+            if hasattr(self.doc_map, "as_object_array"):       # a mapping that can hand over its table at once
+                tab = self.doc_map.as_object_array()
+            else:
+                tab = np.empty(len(self.doc_map), dtype=object)
+                for i in range(len(self.doc_map)):
+                    tab[i] = self.doc_map[i]
             self._doc_table_arr, self._doc_table_key = tab, key
         return self._doc_table_arr
 

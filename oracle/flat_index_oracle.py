@@ -50,7 +50,13 @@ def compute_scores_and_indices(allqueries: torch.Tensor, embeddings_dn: torch.Te
 
     Returns fp16 scores [B, k] (descending) and int64 local row indices [B, k].
     Raises RuntimeError when ``topk > N_local`` exactly like ``torch.topk``.
+    A bf16 matrix (BASELINE configs[3]; not something the reference itself can hold, it always ``.half()``s) is
+    scored by the same two lines with ``.bfloat16()`` — a documented extension, not a restatement.
     """
+    if embeddings_dn.dtype == torch.bfloat16:
+        scores = torch.matmul(allqueries.bfloat16(), embeddings_dn)
+        scores, indices = torch.topk(scores, topk, dim=1)
+        return scores, indices
     scores = torch.matmul(allqueries.half(), embeddings_dn)
     scores, indices = torch.topk(scores, topk, dim=1)
     return scores, indices
@@ -78,6 +84,12 @@ def compute_scores_and_indices_numpy(queries: np.ndarray, embeddings_dn: np.ndar
 def search_knn_single(queries: torch.Tensor, embeddings_dn: torch.Tensor, doc_map: dict, topk: int):
     """Single-rank search_knn: returns (docs, scores) — docs first (src/index.py:158)."""
     scores, indices = compute_scores_and_indices(queries, embeddings_dn, topk)   # :132
+    return search_knn_tail(scores, indices, doc_map, topk)
+
+
+def search_knn_tail(scores: torch.Tensor, indices: torch.Tensor, doc_map, topk: int):
+    """The host part of search_knn after the arithmetic (src/index.py:133-134,152-157): B*k doc_map lookups, the
+    (single-rank: redundant) second topk and the Python re-indexing.  Separate so that bench.py can time it alone."""
     indices = indices.tolist()                                                  # :133
     docs = [[doc_map[x] for x in row] for row in indices]                        # :134
     _, sub = torch.topk(scores, topk, dim=1)                                     # :152

@@ -103,6 +103,17 @@ def worker(rank, world, port, tmpdir, mode):
                              exact[my_rows])
         assert rep["ok"], rep["errors"][:3]
         assert all(d["text"] == f"passage {d['id']}" for row in docs for d in row)
+        # winners owned by the other rank came out of the node-shared passage store, without a collective ...
+        assert "node-shared passage store" in index.last_passage_path
+        own = [d for row in docs for d in row if (int(d["id"]) % world == rank if mode == "round_robin" else
+                                                  index._id_base <= int(d["id"]) < index._id_base + index._store.shape[0])]
+        assert own and all(any(d is v for v in (index.doc_map[(int(d["id"]) - index._id_base) // index._id_stride],)) for d in own), \
+            "own-shard winners must be the doc_map objects themselves"
+        # ... and the all-to-all of pickled winners (ranks on different hosts) returns the same passages
+        os.environ["JSA_MIPS_PASSAGES"] = "a2a"
+        docs_a, scores_a = index.search_knn(my_q, k)
+        os.environ.pop("JSA_MIPS_PASSAGES")
+        assert "all-to-all" in index.last_passage_path and docs_a == docs and scores_a == scores
 
         # empty batch on one rank: still participates in the collectives, gets ([], [])
         docs2, scores2 = index.search_knn(my_q[:0] if rank == 1 else my_q, k)

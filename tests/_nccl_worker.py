@@ -48,6 +48,18 @@ def main():
     s_n, i_n = index.search(my_q, k)
     index._xchg = saved
     assert torch.equal(i_n, i) and torch.equal(s_n, s)
+    # a straggler: the last rank is 15 s late for one search (a checkpoint write, a GC pause).  Its peers' wait
+    # kernels keep polling (the bound is 30 minutes of wall-clock time, nothing traps) and the answer is unchanged.
+    if p2p and os.environ.get("JSA_TEST_STRAGGLER", "1") == "1":
+        import time
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == world - 1:
+            time.sleep(15.0)
+        s_l, i_l = index.search(my_q, k)
+        torch.cuda.synchronize()
+        assert torch.equal(i_l, i) and torch.equal(s_l, s), "search after a 15 s straggler differs"
+        index._xchg.status()
     # back-to-back searches without host syncs: slots alternate, a fast rank may run ahead by one step
     outs = []
     for t in range(40):
@@ -67,6 +79,11 @@ def main():
     ids = torch.tensor([[int(x["id"]) for x in row] for row in docs])
     assert torch.equal(ids, fi[offs[rank]:offs[rank + 1]].cpu())
     assert all(x["text"] == f"passage {x['id']}" for row in docs for x in row)
+    assert "node-shared passage store" in index.last_passage_path          # remote winners: no text over NVLink
+    os.environ["JSA_MIPS_PASSAGES"] = "a2a"                                 # ranks on different hosts: all-to-all of winners
+    docs_a, scores_a = index.search_knn(my_q, k)
+    os.environ.pop("JSA_MIPS_PASSAGES")
+    assert docs_a == docs and scores_a == scores and "all-to-all" in index.last_passage_path
 
     d3, s3, emb = index.search_knn(my_q, 7, return_embeddings=True)                         # build_server/index.py:217-261
     ids3 = torch.tensor([[int(x["id"]) for x in row] for row in d3], device=dev)

@@ -216,6 +216,45 @@ def test_filter_results_by_id(eng):
     assert [len(r) for r in p] == [3, 3] and s[1] == [8.0, 7.0, 6.0]
 
 
+def test_vectorised_filter_matches_the_reference_loop(eng):
+    """Randomised: the id-array filter must give what the reference's per-pair loop gives (restated here)."""
+    import random
+    from importlib import import_module
+    F = import_module("jsa-rag_b200.filtering")
+    rnd = random.Random(7)
+    for trial in range(50):
+        b, kk, topk = rnd.randint(1, 6), rnd.randint(1, 12), rnd.randint(1, 12)
+        docs = [[{"id": str(rnd.randint(0, 5)), "n": j} for j in range(kk)] for _ in range(b)]
+        scores = [[float(kk - j) for j in range(kk)] for _ in range(b)]
+        meta = [{"id": str(rnd.randint(0, 5))} for _ in range(b)]
+        want_p, want_s = [], []
+        for m, ps, ss in zip(meta, docs, scores):                      # src/tasks/base.py:127-146
+            keep = [(p, s) for p, s in zip(ps, ss) if p["id"] != m["id"]]
+            viol = [(p, s) for p, s in zip(ps, ss) if p["id"] == m["id"]]
+            both = keep + viol
+            want_p.append([p for p, _ in both][:topk]); want_s.append([s for _, s in both][:topk])
+        got_p, got_s = F.filter_results_by_id(meta, docs, scores, topk)
+        assert [list(r) for r in got_p] == want_p and [list(r) for r in got_s] == want_s
+        assert all(a is b_ for ra, rb in zip(got_p, want_p) for a, b_ in zip(ra, rb))     # the same dict objects
+    pos, kept = F.filter_positions(np.array([5, 9]), np.array([[5, 1, 5, 2], [1, 2, 3, 4]]), 3)
+    assert pos.tolist() == [[1, 3, 0], [0, 1, 2]] and kept.tolist() == [2, 4]
+    ragged_p, ragged_s = F.filter_results_by_id([{"id": "a"}, {"id": "b"}], [[{"id": "a"}, {"id": "c"}], [{"id": "b"}]],
+                                                [[2.0, 1.0], [3.0]], 2)
+    assert [[d["id"] for d in r] for r in ragged_p] == [["c", "a"], ["b"]]
+
+
+def test_passage_store_round_trip(eng):
+    from importlib import import_module
+    PS = import_module("jsa-rag_b200.passages").PassageStore
+    shards = [[{"id": str(3 * i + r), "title": f"t{i}", "text": "x" * (i % 7)} for i in range(20 + r)] for r in range(3)]
+    st = PS.from_shards(shards)
+    assert [st.shard_len(r) for r in range(3)] == [20, 21, 22]
+    assert st.get(2, 21) == shards[2][21] and st.get(0, 0) == shards[0][0]
+    owners = np.array([0, 2, 1, 1]); rows = np.array([19, 0, 20, 3])
+    assert st.get_many(owners, rows) == [shards[o][r] for o, r in zip(owners, rows)]
+    st.close()
+
+
 def test_peer_exchange_is_optional_and_never_a_cpu_path(eng, monkeypatch):
     """Without an NCCL process group (single process, gloo, CPU) no exchange object is created — callers keep the
     collective path — and the mode switch is read from the environment."""

@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-api-e2e", action="store_true")
+    ap.add_argument("--sweep", default="", help="comma list of batch[:k[:searches_per_step]] measured over ONE resident index, "
+                                                "one JSON line each (BASELINE configs[2..4]); default: the single headline config")
     return ap.parse_args()
 
 
@@ -257,18 +259,15 @@ def parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets):
     sub = eng.B200Index(dtype=tdtype)
     sub._store = index._store[:sub_n]
     sub._set_sharding("round_robin")
-    sub.equal_batch = True
+    sub.equal_batch = index.equal_batch
     ss, si = sub.search(q_sets[0], k)
     if world > 1:
-        all_s = torch.empty((world,) + tuple(ss.shape), dtype=ss.dtype, device=dev)
-        all_i = torch.empty((world,) + tuple(si.shape), dtype=si.dtype, device=dev)
-        all_q = torch.empty((world,) + tuple(q_sets[0].shape), dtype=q_sets[0].dtype, device=dev)
         all_e = torch.empty((world, sub_n, args.dim), dtype=tdtype, device=dev)
-        dist.all_gather_into_tensor(all_s, ss.contiguous())
-        dist.all_gather_into_tensor(all_i, si.contiguous())
-        dist.all_gather_into_tensor(all_q, q_sets[0].contiguous())
         dist.all_gather_into_tensor(all_e, sub._store.contiguous())
-        ss, si, qq = all_s.flatten(0, 1), all_i.flatten(0, 1), all_q.flatten(0, 1)
+        sizes = eng.dist_utils.get_varsize(ss)
+        ss = eng.dist_utils.varsize_all_gather(ss.contiguous(), sizes)      # rank order = query order
+        si = eng.dist_utils.varsize_all_gather(si.contiguous(), sizes)
+        qq = eng.dist_utils.varsize_all_gather(q_sets[0].contiguous(), sizes)
         emb = all_e.permute(1, 0, 2).reshape(sub_n * world, args.dim)     # global id = local * W + rank
         sub.close_exchange()
     else:
@@ -318,247 +317,265 @@ def run_b200(args):
 
     tdtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     n_loc = len(range(rank, args.rows, world))
-    sps = max(1, args.searches_per_step)
     # ---- synthetic shard: rows rank, rank+W, ... of the global index (src/index_io.py:41 sharding) ----
     index = eng.B200Index(dtype=tdtype)
     index.init_embeddings([None] * 0, dim=args.dim)   # doc_map is set for the api_e2e leg only
     index._store = torch.empty(n_loc, args.dim, dtype=tdtype, device=dev)
     index._set_sharding("round_robin")
-    index.equal_batch = True   # every rank contributes batch/N queries
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     for a in range(0, n_loc, 1 << 20):
         c = torch.randn(min(1 << 20, n_loc - a), args.dim, generator=g, device=dev)
         index._store[a:a + c.shape[0]] = torch.nn.functional.normalize(c, dim=1).to(tdtype)
     del c
-    per = args.batch // world
-    q_sets, q_hosts = [], []
-    for j in range(sps):     # one query set per search of a step (posterior / prior queries differ)
-        q_all = torch.nn.functional.normalize(torch.randn(args.batch, args.dim, device=dev,
-                                                          generator=torch.Generator(device=dev).manual_seed(4321 + j)), dim=1)
-        q_mine = q_all[rank * per:(rank + 1) * per].contiguous() if world > 1 else q_all
-        q_sets.append(q_mine)
-        q_hosts.append(q_mine.cpu().pin_memory())
+    def measure(args, first):
+        sps = max(1, args.searches_per_step)
+        sizes = [args.batch // world + (1 if r < args.batch % world else 0) for r in range(world)]
+        offs = [sum(sizes[:r]) for r in range(world + 1)]
+        per = sizes[rank]
+        index.equal_batch = args.batch % world == 0   # every rank contributes batch/N queries (else sizes are exchanged)
+        q_sets, q_hosts = [], []
+        for j in range(sps):     # one query set per search of a step (posterior / prior queries differ)
+            q_all = torch.nn.functional.normalize(torch.randn(args.batch, args.dim, device=dev,
+                                                              generator=torch.Generator(device=dev).manual_seed(4321 + j)), dim=1)
+            q_mine = q_all[offs[rank]:offs[rank + 1]].contiguous() if world > 1 else q_all
+            q_sets.append(q_mine)
+            q_hosts.append(q_mine.cpu().pin_memory())
 
-    engine = index._get_engine()
-    dbg = int(os.environ.get("JSA_MIPS_FLAGS", "0"))   # A/B switches of include/jsa_mips.h (0 = product path)
-    engine.debug_config(8 | dbg, False)   # flag 8: CUDA events around every full-shard scan launch
+        engine = index._get_engine()
+        dbg = int(os.environ.get("JSA_MIPS_FLAGS", "0"))   # A/B switches of include/jsa_mips.h (0 = product path)
+        engine.debug_config(8 | dbg, False)   # flag 8: CUDA events around every full-shard scan launch
 
-    def step():
-        for q in q_sets:
-            out = index.search(q, args.k)
-        return out
+        def step():
+            for q in q_sets:
+                out = index.search(q, args.k)
+            return out
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        def sync_all():
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
 
-    def rank_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
-    engine.scan_times_ms()          # drop warm-up launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    t_wall0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    t_wall1 = time.perf_counter()
-    ms = rank_max(ev0.elapsed_time(ev1))
-    scan_ms = engine.scan_times_ms()
-    p2p = bool(getattr(index, "_xchg", None))
-    # own kernels per step: the local search + (push, wait+merge) with the peer exchange, or the merge after NCCL
-    p2p_q = bool(getattr(index, "_xchg_q", None))
-    launches = sps * (engine.last_launch_count() + (((2 if p2p else 1) + (2 if p2p_q else 0)) if world > 1 else 0))
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-
-    # ---- sustained load: the same step back to back for >= sustained_seconds (the timed region above is a burst
-    #      of a fraction of a second; a training loop sits at the 1 kW power cap) ----
-    sustained = None
-    if args.sustained_seconds > 0:
-        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / max(1e-3, ms / args.steps)) + 1)
-        if world > 1:
-            t = torch.tensor([n_sus], device=dev)
+        def rank_max(x):
+            if world == 1:
+                return x
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            n_sus = int(t.item())
-        sampler2 = ClockSampler(local_rank)
-        if rank == 0:
-            sampler2.start()
-        sync_all()
-        engine.scan_times_ms()
-        w0 = time.perf_counter()
-        ev0.record()
-        for it in range(n_sus):
+            return float(t.item())
+
+        for _ in range(max(args.warmup, 3)):
             step()
-            if it % 64 == 63:
-                engine.scan_times_ms()          # keep only the tail of the run (at most 256 launches are recorded)
+        sync_all()
+        engine.scan_times_ms()          # drop warm-up launches
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t_wall0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
         ev1.record()
         sync_all()
-        w1 = time.perf_counter()
-        sus_ms = rank_max(ev0.elapsed_time(ev1))
-        sus_scan = engine.scan_times_ms()
-        sus_clocks = sampler2.stop(w0 + 0.5 * (w1 - w0), w1) if rank == 0 else None   # second half: settled clocks
-        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "value": args.batch * sps * n_sus / (sus_ms * 1e-3),
-                     "ms_per_step": sus_ms / n_sus, "avg_launch_ms": (sum(sus_scan) / len(sus_scan)) if sus_scan else None,
-                     "clocks": sus_clocks}
+        t_wall1 = time.perf_counter()
+        ms = rank_max(ev0.elapsed_time(ev1))
+        scan_ms = engine.scan_times_ms()
+        p2p = bool(getattr(index, "_xchg", None))
+        # own kernels per step: the local search + (push, wait+merge) with the peer exchange, or the merge after NCCL
+        p2p_q = bool(getattr(index, "_xchg_q", None))
+        launches = sps * (engine.last_launch_count() + (((2 if p2p else 1) + (2 if p2p_q else 0)) if world > 1 else 0))
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
-    # ---- end to end through the public API with HOST buffers (H2D of the queries + D2H of the result) ----
-    res_s = torch.empty(per if world > 1 else args.batch, args.k, dtype=torch.float32).pin_memory()
-    res_i = torch.empty(per if world > 1 else args.batch, args.k, dtype=torch.int64).pin_memory()
+        # ---- sustained load: the same step back to back for >= sustained_seconds (the timed region above is a burst
+        #      of a fraction of a second; a training loop sits at the 1 kW power cap) ----
+        sustained = None
+        if args.sustained_seconds > 0:
+            n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / max(1e-3, ms / args.steps)) + 1)
+            if world > 1:
+                t = torch.tensor([n_sus], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                n_sus = int(t.item())
+            sampler2 = ClockSampler(local_rank)
+            if rank == 0:
+                sampler2.start()
+            sync_all()
+            engine.scan_times_ms()
+            w0 = time.perf_counter()
+            ev0.record()
+            for it in range(n_sus):
+                step()
+                if it % 64 == 63:
+                    engine.scan_times_ms()          # keep only the tail of the run (at most 256 launches are recorded)
+            ev1.record()
+            sync_all()
+            w1 = time.perf_counter()
+            sus_ms = rank_max(ev0.elapsed_time(ev1))
+            sus_scan = engine.scan_times_ms()
+            sus_clocks = sampler2.stop(w0 + 0.5 * (w1 - w0), w1) if rank == 0 else None   # second half: settled clocks
+            sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "value": args.batch * sps * n_sus / (sus_ms * 1e-3),
+                         "ms_per_step": sus_ms / n_sus, "avg_launch_ms": (sum(sus_scan) / len(sus_scan)) if sus_scan else None,
+                         "clocks": sus_clocks}
 
-    graphed = None
-    engine.debug_config(dbg, False)   # no event records inside the captured graph
-    if world > 1:
-        # a ~1 ms distributed search is sensitive to ~150 us of Python/launch overhead per step: replay a CUDA
-        # graph of the same public search (collectives included); fall back to the eager call if capture fails
-        okf = torch.ones(1, device=dev)
-        try:
-            graphed = index.make_graphed_search(per, args.k)
-        except Exception as ex:  # noqa: BLE001
-            okf.zero_()
-            sys.stderr.write(f"[rank {rank}] CUDA-graph capture unavailable, eager e2e path: {ex}\n")
-        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-        if okf.item() == 0:
-            if graphed is not None:
-                graphed.release()
+        # ---- end to end through the public API with HOST buffers (H2D of the queries + D2H of the result) ----
+        res_s = torch.empty(per, args.k, dtype=torch.float32).pin_memory()
+        res_i = torch.empty(per, args.k, dtype=torch.int64).pin_memory()
+
+        graphed = None
+        engine.debug_config(dbg, False)   # no event records inside the captured graph
+        if world > 1 and index.equal_batch:
+            # a ~1 ms distributed search is sensitive to ~150 us of Python/launch overhead per step: replay a CUDA
+            # graph of the same public search (collectives included); fall back to the eager call if capture fails
+            okf = torch.ones(1, device=dev)
+            try:
+                graphed = index.make_graphed_search(per, args.k)
+            except Exception as ex:  # noqa: BLE001
+                okf.zero_()
+                sys.stderr.write(f"[rank {rank}] CUDA-graph capture unavailable, eager e2e path: {ex}\n")
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if okf.item() == 0:
+                if graphed is not None:
+                    graphed.release()
+                graphed = None
+
+        def e2e_step():
+            for qh in q_hosts:
+                if world == 1:
+                    engine.search_host(qh, args.k, out=(res_s, res_i))          # C ABI: mips_search_host
+                else:
+                    if graphed is not None:
+                        s, i = graphed(qh)
+                    else:
+                        s, i = index.search(qh.to(dev, non_blocking=True), args.k)
+                    res_s.copy_(s, non_blocking=True); res_i.copy_(i, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+
+        graphed_used = graphed is not None
+        for _ in range(3):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        sync_all()
+        e2e_s = rank_max(time.perf_counter() - t0)
+        if graphed is not None:
+            graphed.release()          # graphs that captured NCCL kernels must die before the communicator
             graphed = None
 
-    def e2e_step():
-        for qh in q_hosts:
-            if world == 1:
-                engine.search_host(qh, args.k, out=(res_s, res_i))          # C ABI: mips_search_host
-            else:
-                if graphed is not None:
-                    s, i = graphed(qh)
+        # ---- the reference-facing call itself: search_knn -> (docs, scores) as nested Python lists ----
+        api = None
+        if not args.no_api_e2e:
+            if not isinstance(index.doc_map, PooledDocMap):
+                index.doc_map = PooledDocMap(n_loc)
+                index.refresh_passages()
+            q_dev = q_sets[0]
+            for _ in range(2):
+                index.search_knn(q_dev, args.k)
+            sync_all()
+            n_api = max(3, min(args.steps, 20))
+            t0 = time.perf_counter()
+            for _ in range(n_api):
+                docs, scores = index.search_knn(q_dev, args.k)
+            sync_all()
+            api_s = rank_max(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            for _ in range(n_api):
+                index.search(q_dev, args.k)
+            sync_all()
+            dev_s = rank_max(time.perf_counter() - t0)
+            assert len(docs) == q_dev.shape[0] and (not docs or (len(docs[0]) == args.k and isinstance(scores[0][0], float)))
+            api = {"value": args.batch * n_api / api_s, "unit": UNIT, "ms_per_search": 1e3 * api_s / n_api,
+                   "host_tail_ms": 1e3 * (api_s - dev_s) / n_api,
+                   "what": "B200Index.search_knn (reference signature, src/index.py:123-158): device search + D2H + passage "
+                           "dicts for the k winners of this rank's queries + fp16-rounded score lists",
+                   "passages": getattr(index, "last_passage_path", None)}
+
+        parity = None if args.no_parity else parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets)
+
+        if rank == 0:
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+            n_launch = max(1, len(scan_ms))
+            scan_avg_ms = sum(scan_ms) / n_launch
+            launches_per_step = max(1, len(scan_ms) // max(1, args.steps))
+            if args.batch >= 256:
+                # several query blocks per launch: the scan is tensor-core bound (BASELINE.md crossover B* ~ 215)
+                bound, unit = "tensor", "TFLOP/s"
+                per_launch = 2.0 * args.batch * sps * n_loc * args.dim / launches_per_step   # flops per launch (average)
+                scale = 1e12
+                if "bf16_tflops_sustained" in peaks:
+                    peak, peak_src = float(peaks["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
                 else:
-                    s, i = index.search(qh.to(dev, non_blocking=True), args.k)
-                res_s.copy_(s, non_blocking=True); res_i.copy_(i, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-
-    for _ in range(3):
-        e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    sync_all()
-    e2e_s = rank_max(time.perf_counter() - t0)
-    if graphed is not None:
-        graphed.release()          # graphs that captured NCCL kernels must die before the communicator
-        graphed = None
-
-    # ---- the reference-facing call itself: search_knn -> (docs, scores) as nested Python lists ----
-    api = None
-    if not args.no_api_e2e:
-        index.doc_map = PooledDocMap(n_loc)
-        q_dev = q_sets[0]
-        for _ in range(2):
-            index.search_knn(q_dev, args.k)
-        sync_all()
-        n_api = max(3, min(args.steps, 20))
-        t0 = time.perf_counter()
-        for _ in range(n_api):
-            docs, scores = index.search_knn(q_dev, args.k)
-        sync_all()
-        api_s = rank_max(time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        for _ in range(n_api):
-            index.search(q_dev, args.k)
-        sync_all()
-        dev_s = rank_max(time.perf_counter() - t0)
-        assert len(docs) == q_dev.shape[0] and len(docs[0]) == args.k and isinstance(scores[0][0], float)
-        api = {"value": args.batch * n_api / api_s, "unit": UNIT, "ms_per_search": 1e3 * api_s / n_api,
-               "host_tail_ms": 1e3 * (api_s - dev_s) / n_api,
-               "what": "B200Index.search_knn (reference signature, src/index.py:123-158): device search + D2H + passage "
-                       "dicts for the k winners of this rank's queries + fp16-rounded score lists",
-               "passages": getattr(index, "last_passage_path", None)}
-
-    parity = None if args.no_parity else parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets)
-
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
-        n_launch = max(1, len(scan_ms))
-        scan_avg_ms = sum(scan_ms) / n_launch
-        launches_per_step = max(1, len(scan_ms) // max(1, args.steps))
-        if args.batch >= 256:
-            # several query blocks per launch: the scan is tensor-core bound (BASELINE.md crossover B* ~ 215)
-            bound, unit = "tensor", "TFLOP/s"
-            per_launch = 2.0 * args.batch * sps * n_loc * args.dim / launches_per_step   # flops per launch (average)
-            scale = 1e12
-            if "bf16_tflops_sustained" in peaks:
-                peak, peak_src = float(peaks["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+                    peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+                algo_key = "algorithmic_flops_per_launch"
             else:
-                peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
-            algo_key = "algorithmic_flops_per_launch"
-        else:
-            bound, unit = "hbm", "GB/s"
-            per_launch = float(n_loc * args.dim * 2)                                      # index bytes, read once per launch
-            scale = 1e9
-            if "hbm_gbs" in peaks:
-                peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+                bound, unit = "hbm", "GB/s"
+                per_launch = float(n_loc * args.dim * 2)                                      # index bytes, read once per launch
+                scale = 1e9
+                if "hbm_gbs" in peaks:
+                    peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+                else:
+                    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+                algo_key = "algorithmic_bytes_per_launch"
+            achieved = per_launch / (scan_avg_ms * 1e-3) / scale if scan_ms else None
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                ent = tj.get("per_launch", {}).get(f"rows{n_loc}_dim{args.dim}_b{args.batch}_k{args.k}_{args.dtype}")
+                if ent:
+                    traffic, traffic_src = ent["dram_bytes"], ent["source"]
+            roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel": "mips::mips_scan_pair_kernel (full-shard pass, CTA pairs)" if args.batch > 128 and not (dbg & (128 | 32))
+                              else "mips::mips_scan_kernel (full-shard pass)",
+                    "peak_source": peak_src, algo_key: per_launch, "avg_launch_ms": scan_avg_ms,
+                    "launches_timed": len(scan_ms), "launches_per_step": launches_per_step}
+            if sustained is not None:
+                sa = per_launch / (sustained["avg_launch_ms"] * 1e-3) / scale if sustained["avg_launch_ms"] else None
+                roof["sustained"] = {"achieved": sa, "frac": (sa / peak) if sa else None, "unit": unit,
+                                     "avg_launch_ms": sustained["avg_launch_ms"], "seconds": sustained["seconds"],
+                                     "steps": sustained["steps"], "value": sustained["value"], "value_unit": UNIT,
+                                     "sm_mhz": (sustained["clocks"] or {}).get("sm_mhz"),
+                                     "reasons": (sustained["clocks"] or {}).get("reasons")}
+            line = {
+                "metric": METRIC, "value": args.batch * sps * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
+                "config": dict(workload(args, world), **({"exchange": "nvlink peer stores (queries and candidates) + wait-and-merge kernel" if p2p
+                                                          else "nccl all-gather + merge kernel"} if world > 1 else {})),
+                "e2e": {"value": args.batch * sps * args.steps / e2e_s, "unit": UNIT,
+                        "path": "mips_search_host (C ABI, host buffers)" if world == 1 else
+                                ("B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)"
+                                 if graphed_used else "B200Index.search (public distributed API, eager)"),
+                        "h2d_bytes_per_step": int(args.batch * args.dim * 4 * sps),
+                        "d2h_bytes_per_step": int(args.batch * args.k * 12 * sps)},
+                "api_e2e": api,
+                "gpu_launches": launches * args.steps,
+                "clocks": clocks,
+                "roofline": roof,
+                "parity": parity,
+            }
+            if world == 1 and not args.no_cpu_baseline and first:
+                cb = cpu_reference_rate(args, reps=3)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "search_knn")}
             else:
-                peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-            algo_key = "algorithmic_bytes_per_launch"
-        achieved = per_launch / (scan_avg_ms * 1e-3) / scale if scan_ms else None
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            ent = tj.get("per_launch", {}).get(f"rows{n_loc}_dim{args.dim}_b{args.batch}_k{args.k}_{args.dtype}")
-            if ent:
-                traffic, traffic_src = ent["dram_bytes"], ent["source"]
-        roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "mips::mips_scan_pair_kernel (full-shard pass, CTA pairs)" if args.batch > 128 and not (dbg & (128 | 32))
-                          else "mips::mips_scan_kernel (full-shard pass)",
-                "peak_source": peak_src, algo_key: per_launch, "avg_launch_ms": scan_avg_ms,
-                "launches_timed": len(scan_ms), "launches_per_step": launches_per_step}
-        if sustained is not None:
-            sa = per_launch / (sustained["avg_launch_ms"] * 1e-3) / scale if sustained["avg_launch_ms"] else None
-            roof["sustained"] = {"achieved": sa, "frac": (sa / peak) if sa else None, "unit": unit,
-                                 "avg_launch_ms": sustained["avg_launch_ms"], "seconds": sustained["seconds"],
-                                 "steps": sustained["steps"], "value": sustained["value"], "value_unit": UNIT,
-                                 "sm_mhz": (sustained["clocks"] or {}).get("sm_mhz"),
-                                 "reasons": (sustained["clocks"] or {}).get("reasons")}
-        line = {
-            "metric": METRIC, "value": args.batch * sps * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
-            "config": dict(workload(args, world), **({"exchange": "nvlink peer stores (queries and candidates) + wait-and-merge kernel" if p2p
-                                                      else "nccl all-gather + merge kernel"} if world > 1 else {})),
-            "e2e": {"value": args.batch * sps * args.steps / e2e_s, "unit": UNIT,
-                    "path": "mips_search_host (C ABI, host buffers)" if world == 1 else
-                            "B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)",
-                    "h2d_bytes_per_step": int(sum(q.numel() for q in q_hosts) * 4 * world),
-                    "d2h_bytes_per_step": int((res_s.numel() * 4 + res_i.numel() * 8) * world * sps)},
-            "api_e2e": api,
-            "gpu_launches": launches * args.steps,
-            "clocks": clocks,
-            "roofline": roof,
-            "parity": parity,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            del index._store
-            cb = cpu_reference_rate(args, reps=3)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "search_knn")}
-        else:
-            line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+                line["cpu_baseline"] = None
+            print(json.dumps(line), flush=True)
+
+    configs = [(args.batch, args.k, args.searches_per_step)]
+    if args.sweep:
+        configs = []
+        for item in args.sweep.split(","):
+            f = [int(x) for x in item.split(":")]
+            configs.append((f[0], f[1] if len(f) > 1 else args.k, f[2] if len(f) > 2 else 1))
+    import copy
+    for ci, (b_, k_, sps_) in enumerate(configs):
+        a = copy.copy(args)
+        a.batch, a.k, a.searches_per_step = b_, k_, sps_
+        measure(a, ci == 0)
     if world > 1:
         # the result line is out; a teardown problem must never stall the caller
         guard = threading.Timer(30.0, os._exit, (0,))
@@ -573,6 +590,10 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    if os.environ.get("JSA_BENCH_WATCHDOG_S"):
+        # debugging aid: dump every thread's Python stack and exit if the run is still going after that many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["JSA_BENCH_WATCHDOG_S"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -208,6 +208,14 @@ int mips_search_host(mips_handle* h, const float* host_queries, int batch, int k
 int mips_search_host_async(mips_handle* h, const float* host_queries, int batch, int k, int normalize,
                            float* host_scores, int64_t* host_ids, void* stream);
 
+/*
+ * Host-only helper of the server's JSON route: parses a JSON list of decimal numbers ("[0.12, -3e-4, ...]", the
+ * brackets optional) into fp32.  Returns the count, or < 0 (-2: a token that is not a plain number, -3: more than
+ * max_out numbers) — callers then fall back to a general JSON parser.
+ * Replaces: torch.tensor(request.query_embs) over a pydantic-validated list (build_server/server_start.py:186).
+ */
+int64_t mips_parse_float_list(const char* text, size_t len, float* out, int64_t max_out);
+
 /* Number of kernels the last mips_search_local / mips_search_host on this handle launched. */
 int mips_last_launch_count(const mips_handle* h);
 

@@ -57,6 +57,7 @@ SYMBOLS = {
                                  c_void_p]),
     "mips_search_host_async": (c_int, [c_void_p, POINTER(c_float), c_int, c_int, c_int, POINTER(c_float), POINTER(c_int64),
                                        c_void_p]),
+    "mips_parse_float_list": (c_int64, [c_char_p, c_size_t, POINTER(c_float), c_int64]),
     "mips_last_launch_count": (c_int, [c_void_p]),
     "mips_debug_config": (c_int, [c_void_p, c_int, c_void_p]),
     "mips_debug_num_stats": (c_int, []),

@@ -9,7 +9,7 @@ OUT = os.path.join(HERE, "libjsa_mips.so")
 SOURCES = ["scan.cu", "merge.cu", "rerank.cu", "exchange.cu", "api.cu"]
 HEADERS = ["internal.h", "ptx.cuh", os.path.join("..", "..", "include", "jsa_mips.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-lcudart"]
+              "-Xcompiler", "-fPIC", "-shared", "-lcudart", "-ldl"]
 
 
 def needs_build() -> bool:

@@ -5,6 +5,8 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +57,16 @@ struct mips_handle {
 namespace mips {
 bool g_use_pdl = []() { const char* e = getenv("JSA_MIPS_PDL"); return !(e && e[0] == '0'); }();
 }
+
+namespace {
+// NVTX ranges around the launches of a search (JSA_MIPS_NVTX=1; off by default: a range is two extra driver calls)
+const bool g_nvtx = []() { const char* e = getenv("JSA_MIPS_NVTX"); return e && e[0] == '1'; }();
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(g_nvtx) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+}  // namespace
 
 namespace {
 
@@ -341,8 +353,12 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   void* qbuf = ws + w.q_off;
   const int bpad = static_cast<int>(align_up(batch, 2 * kNQ));
 
-  CUDA_TRY(h, launch_prep_queries(queries, q_dtype, q_ld, batch, bpad, h->dim, h->dtype, normalize, qbuf,
-                                  static_cast<uint32_t*>(h->sync), st));
+  NvtxRange nv_search("mips.search_local");
+  {
+    NvtxRange nv("mips.prep");
+    CUDA_TRY(h, launch_prep_queries(queries, q_dtype, q_ld, batch, bpad, h->dim, h->dtype, normalize, qbuf,
+                                    static_cast<uint32_t*>(h->sync), st));
+  }
   h->last_launches++;
 
   CUtensorMap tmap_q;
@@ -459,6 +475,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     }
     ++n_launch;
     for (int lv = 0; lv < n_levels; ++lv) {
+      NvtxRange nv("mips.sampled_prepass");
       ScanParams pp = p;
       pp.num_tiles = levels[lv] * nslots < num_tiles ? levels[lv] * nslots : num_tiles;
       pp.stats = nullptr;
@@ -469,8 +486,12 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     }
     const bool timed = (h->dbg_flags & kDbgTimeScan) && h->timing_ready && h->n_timed < mips_handle::kMaxTimed;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev0[h->n_timed], st));
-    CUDA_TRY(h, scan(tmap_e, tmap_q, p, launch_grid, smem_bytes, st));
+    {
+      NvtxRange nv(pair ? "mips.scan_pair" : "mips.scan");
+      CUDA_TRY(h, scan(tmap_e, tmap_q, p, launch_grid, smem_bytes, st));
+    }
     if (timed) { CUDA_TRY(h, cudaEventRecord(h->ev1[h->n_timed], st)); h->n_timed++; }
+    NvtxRange nv_sel("mips.select");
     CUDA_TRY(h, launch_select(p.cand, p.part_cnt, nslots, nblk, p.cap, p.batch, k, h->id_base, h->id_stride,
                               out_scores + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k, st));
     h->last_launches += 2;
@@ -573,6 +594,71 @@ int mips_search_host_async(mips_handle* h, const float* host_queries, int batch,
 }
 
 int mips_last_launch_count(const mips_handle* h) { return h ? h->last_launches : 0; }
+
+// JSON float list -> fp32 (host only).  The reference's wire format sends the query matrix as a flat list of
+// decimal floats (build_server/server_start.py:18-21,186): 65 536 numbers of ~18 digits for a 64 x 1024 batch,
+// which Python's json needs ~40 ms to parse.  This is a plain decimal scanner: up to 19 significant digits are
+// accumulated exactly in 64 bits and scaled by a power of ten in double precision (exact powers up to 1e22); longer
+// mantissas or exponents outside that range go through strtod.  The result can differ from a correctly rounded
+// strtod by one double ulp before the rounding to fp32 — far below the fp16 rounding the queries undergo next.
+int64_t mips_parse_float_list(const char* text, size_t len, float* out, int64_t max_out) {
+  static const double kPow10[] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                  1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  if (!text || !out) return -1;
+  const char* p = text;
+  const char* end = text + len;
+  int64_t n = 0;
+  while (p < end) {
+    while (p < end && (*p == ' ' || *p == ',' || *p == '\n' || *p == '\t' || *p == '\r' || *p == '[')) ++p;
+    if (p >= end || *p == ']') break;
+    const char* start = p;
+    bool neg = false;
+    if (*p == '-') { neg = true; ++p; } else if (*p == '+') { ++p; }
+    uint64_t mant = 0;
+    int digits = 0, dropped = 0, frac = 0;
+    bool any = false, seen_dot = false;
+    for (; p < end; ++p) {
+      const char c = *p;
+      if (c >= '0' && c <= '9') {
+        any = true;
+        if (digits < 19) { mant = mant * 10 + static_cast<uint64_t>(c - '0'); if (mant != 0 || seen_dot) ++digits; else digits = 0; if (seen_dot) ++frac; }
+        else { ++dropped; if (seen_dot) { /* beyond 19 digits: ignored fraction digits */ } else { --frac; } }
+      } else if (c == '.' && !seen_dot) {
+        seen_dot = true;
+      } else {
+        break;
+      }
+    }
+    int exp10 = 0;
+    if (p < end && (*p == 'e' || *p == 'E')) {
+      const char* q = p + 1;
+      bool eneg = false;
+      if (q < end && (*q == '-' || *q == '+')) { eneg = *q == '-'; ++q; }
+      int e = 0;
+      bool edig = false;
+      for (; q < end && *q >= '0' && *q <= '9'; ++q) { edig = true; if (e < 10000) e = e * 10 + (*q - '0'); }
+      if (edig) { exp10 = eneg ? -e : e; p = q; }
+    }
+    if (!any) return -2;                 // not a number (NaN / Infinity / garbage): the caller falls back to json
+    if (n >= max_out) return -3;
+    const int scale = exp10 - frac;
+    double v;
+    if (dropped == 0 && scale >= -22 && scale <= 22) {
+      v = static_cast<double>(mant);
+      v = scale < 0 ? v / kPow10[-scale] : v * kPow10[scale];
+    } else {
+      char buf[64];
+      const size_t l = static_cast<size_t>(p - start);
+      if (l >= sizeof(buf)) return -2;
+      memcpy(buf, start, l);
+      buf[l] = 0;
+      v = strtod(buf, nullptr);
+      neg = false;                       // strtod already applied the sign
+    }
+    out[n++] = static_cast<float>(neg ? -v : v);
+  }
+  return n;
+}
 
 int mips_debug_config(mips_handle* h, int flags, void* stats_dev) {
   if (!h) return MIPS_EINVAL;

@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from . import dist_utils
+from .tracing import SearchTimer, nvtx_range
 
 EMBEDDINGS_DIM: int = 768  # reference src/retrievers.py:14
 
@@ -70,7 +71,11 @@ class B200Index(object):
         # reference's training loop; evaluate.py:49-54 pads iterators to keep ranks in step) -> the size
         # exchange (a collective + a host sync, src/index.py:129-130) is skipped
         self.equal_batch = False
+        # search_knn leaves its CUDA-synchronised timings here ("runtime/search", ".../search_device",
+        # ".../search_host_tail", seconds); set ``iter_stats`` to the trainer's dict and the reference's
+        # ``runtime/search`` entry (src/rag.py:170) is filled with the same (value, count) tuples
         self.last_search_stats = {}
+        self.iter_stats = None
 
     # ------------------------------------------------------------------ storage
     def _storage_device(self) -> torch.device:
@@ -256,7 +261,8 @@ class B200Index(object):
             if xq is not None:                                                     # NVLink peer stores, no collective call
                 allqueries = xq.gather(queries).view(w * sizes[0], queries.shape[1])
         if allqueries is None:
-            allqueries = dist_utils.varsize_all_gather(queries, sizes)             # src/index.py:128
+            with nvtx_range("mips.query_gather"):
+                allqueries = dist_utils.varsize_all_gather(queries, sizes)         # src/index.py:128
         offs = np.cumsum([0] + sizes)
         if allqueries.shape[0] == 0:
             return (torch.empty(0, topk, device=queries.device),
@@ -271,15 +277,17 @@ class B200Index(object):
             n_local = 0 if self._store is None else int(self._store.shape[0])
             if topk > n_local:
                 raise RuntimeError("selected index k out of range")
-            self._get_engine().search(allqueries, topk, normalize=normalize, out=(ls[0], li[0]))   # src/index.py:132
+            with nvtx_range("mips.local_search"):
+                self._get_engine().search(allqueries, topk, normalize=normalize, out=(ls[0], li[0]))   # src/index.py:132
             xchg = self._peer_exchange(int(buf.shape[1]), buf.device)
-            if xchg is not None:
-                # NVLink peer stores into every rank's slot + wait-and-merge kernel (replaces :135-157)
-                ms, mi = xchg.merge(buf[0], bt, topk, topk)
-            else:
-                gathered = torch.empty((w, buf.shape[1]), dtype=torch.uint8, device=buf.device)
-                torch.distributed.all_gather_into_tensor(gathered, buf[0])                         # replaces :139-142
-                ms, mi = merge_packed(gathered, bt, topk, topk)                                      # replaces :143-157
+            with nvtx_range("mips.exchange_merge"):
+                if xchg is not None:
+                    # NVLink peer stores into every rank's slot + wait-and-merge kernel (replaces :135-157)
+                    ms, mi = xchg.merge(buf[0], bt, topk, topk)
+                else:
+                    gathered = torch.empty((w, buf.shape[1]), dtype=torch.uint8, device=buf.device)
+                    torch.distributed.all_gather_into_tensor(gathered, buf[0])                     # replaces :139-142
+                    ms, mi = merge_packed(gathered, bt, topk, topk)                                  # replaces :143-157
         else:
             ls, li = self._local_search(allqueries, topk, normalize)               # src/index.py:132
             gs, gi = dist_utils.all_gather_candidates(ls, li)                      # replaces :139-142
@@ -475,9 +483,17 @@ class B200Index(object):
         first — as nested Python lists, rows sorted by descending score; with
         ``return_embeddings=True`` also the passage embeddings ``[b, k, dim]`` like the
         build_server twin (build_server/index.py:217-261)."""
-        scores, ids = self.search(queries, topk)
-        # (every rank takes part in the passage exchange, also one whose own batch is empty)
-        docs = self._resolve_docs(ids) if (scores.shape[0] > 0 or self._any_rank_has_queries) else []
+        dev = self._store.device if self._store is not None and self._store.is_cuda else None
+        with SearchTimer(dev) as timer:
+            scores, ids = self.search(queries, topk)
+            timer.device_done()
+            # (every rank takes part in the passage exchange, also one whose own batch is empty)
+            with nvtx_range("mips.resolve_passages"):
+                docs = self._resolve_docs(ids) if (scores.shape[0] > 0 or self._any_rank_has_queries) else []
+        self.last_search_stats = timer.stats()
+        if isinstance(self.iter_stats, dict):
+            for key, val in self.last_search_stats.items():
+                self.iter_stats[key] = (val, 1)                  # src/rag.py:170 convention
         if scores.shape[0] == 0:
             if return_embeddings:
                 emb = self._gather_embeddings(ids) if self._any_rank_has_queries else None

@@ -123,3 +123,27 @@ def test_server_search_matches_faiss_semantics(eng, tmp_path):
     assert docs2 == docs and np.allclose(np.array(scores2), np.array(scores))
     with pytest.raises(RuntimeError, match="selected index k out of range"):
         index.search_knn(torch.from_numpy(q), 301)
+
+
+def test_retrieve_request_parser(eng):
+    """The hand-written body parser of POST /retrieve accepts what the reference's pydantic model accepts
+    (build_server/server_start.py:18-21) and rejects the rest with 422."""
+    import json
+    from importlib import import_module
+    from fastapi import HTTPException
+    S = import_module("jsa-rag_b200.server")
+    rng = np.random.default_rng(1)
+    q = rng.standard_normal(6 * 16).astype(np.float32)
+    r = S.parse_retrieve_request(json.dumps({"query_embs": q.tolist(), "bsz": 6, "topk": 5}).encode())
+    assert r["bsz"] == 6 and r["topk"] == 5 and np.array_equal(r["query_embs"], q)          # C scanner, exact
+    r = S.parse_retrieve_request(json.dumps({"topk": 3, "query_embs": [1, 2.5, -3e-2, 4E1]}).encode())
+    assert r["bsz"] == 1 and r["query_embs"].tolist() == [1.0, 2.5, np.float32(-0.03), 40.0]
+    r = S.parse_retrieve_request(b'{"query_embs": [[1.0, 2.0], [3.0, 4.0]], "bsz": 2}')       # nested: general json path
+    assert r["query_embs"].tolist() == [1.0, 2.0, 3.0, 4.0] and r["topk"] == 10
+    r = S.parse_retrieve_request(b'{"query_embs": [1.0, NaN], "bsz": 1}')                     # not a plain number: json path
+    assert np.isnan(r["query_embs"][1])
+    for bad in (b"not json", b"[1, 2]", b'{"bsz": 2}', b'{"query_embs": "x"}', b'{"query_embs": [1, 2, 3], "bsz": 2}',
+                b'{"query_embs": [1.0], "bsz": 1.5}', b'{"query_embs": [1.0], "bsz": 0}', b'{"query_embs": ["a"]}'):
+        with pytest.raises(HTTPException) as ei:
+            S.parse_retrieve_request(bad)
+        assert ei.value.status_code == 422

@@ -71,7 +71,7 @@ struct NvtxRange {
 namespace {
 
 // layout of mips_handle::sync: [0] search token | kSyncFlagOff: uint32 flag per CTA | + kSyncSeedOff: uint64 seed tags
-constexpr size_t kSyncFlagOff = 256, kSyncSeedOff = 4096;
+constexpr size_t kSyncFlagOff = 256, kSyncSeedOff = 4096, kSyncProgBytes = 1024;   // progress words: one per CTA pair
 
 std::string g_create_err;
 std::mutex g_mu;
@@ -233,7 +233,7 @@ int mips_create(mips_handle** out, int device, int dim, int index_dtype) {
     cudaGetLastError();
     if (const char* e2 = getenv("JSA_MIPS_PAIRS")) { if (e2[0] == '0') h->max_pairs = 0; }
   }
-  constexpr size_t kSyncBytes = kSyncFlagOff + kSyncSeedOff + kMaxQBlocks * kNQ * sizeof(uint64_t);
+  constexpr size_t kSyncBytes = kSyncFlagOff + kSyncSeedOff + kMaxQBlocks * kNQ * sizeof(uint64_t) + kSyncProgBytes;
   e = cudaMalloc(&h->sync, kSyncBytes);
   if (e == cudaSuccess) e = cudaMemset(h->sync, 0, kSyncBytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -399,7 +399,7 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
   // one launch carries 1 or 2 pair blocks (256 / 512 queries; with 74 pairs, 2 blocks x 37 tile sequences).
   constexpr int kMaxBlocks = 4;
   const bool pairs_ok = h->layout == 1 && h->max_pairs >= 1 && !(h->dbg_flags & (kDbgNoPair | kDbgOneBlock));
-  int n_launch = 0;
+  int n_launch = 0, scan_seq = 0;
   for (int q0 = 0; q0 < batch;) {
     const int rem = batch - q0;
     const bool pair = pairs_ok && rem > kNQ;
@@ -427,6 +427,13 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     p.m64 = (!pair && nblk == 1 && p.batch <= 64 && !(h->dbg_flags & kDbgForceM128)) ? 1 : 0;
     p.idesc = ptx::make_idesc_f16(pair ? 2 * kNQ : (p.m64 ? 64 : kNQ), kTileN, h->dtype == MIPS_DTYPE_BF16 ? 1 : 0) |
               (p.b_mn ? (1u << 16) : 0u);   // bit 16: B operand is MN-major
+    p.token = static_cast<const uint32_t*>(h->sync);
+    p.progress = nullptr;
+    static const int lock_window = []() { const char* e = getenv("JSA_MIPS_LOCK_WINDOW"); const int v = e ? atoi(e) : kLockWindow; return v < 1 ? 1 : v; }();
+    p.lock_window = lock_window;
+    if (pair && nblk > 2 && !(h->dbg_flags & kDbgNoLockstep) && static_cast<size_t>(launch_grid / 2) * 8 <= kSyncProgBytes)
+      p.progress = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(h->sync) + kSyncFlagOff + kSyncSeedOff +
+                                                         kMaxQBlocks * kNQ * sizeof(uint64_t));
     p.num_stages = pair ? h->pair_stages : h->num_stages;
     p.chunks_per_stage = pair ? h->num_kchunks : h->chunks_per_stage;
     const CUtensorMap& tmap_e = pair ? h->tmap_e_half : h->tmap_e;
@@ -468,7 +475,6 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       p.sample_tiles = levels[n_levels - 1];
       p.launch_idx = n_launch;
       p.top = reinterpret_cast<uint32_t*>(ws + w.top_off);
-      p.token = static_cast<const uint32_t*>(h->sync);
       p.top_flag = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->sync) + kSyncFlagOff);
       p.seed_tag = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(h->sync) + kSyncFlagOff + kSyncSeedOff);
       n_levels = 0;
@@ -479,11 +485,13 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
       ScanParams pp = p;
       pp.num_tiles = levels[lv] * nslots < num_tiles ? levels[lv] * nslots : num_tiles;
       pp.stats = nullptr;
+      pp.scan_seq = (scan_seq++) & 4095;
       CUDA_TRY(h, scan(tmap_e, tmap_q, pp, launch_grid, smem_bytes, st));
       CUDA_TRY(h, launch_select(p.cand, p.part_cnt, nslots, nblk, p.cap, p.batch, k, 0, 1, seed_scores, seed_ids, st));
       h->last_launches += 2;
       p.seed = seed_scores;
     }
+    p.scan_seq = (scan_seq++) & 4095;
     const bool timed = (h->dbg_flags & kDbgTimeScan) && h->timing_ready && h->n_timed < mips_handle::kMaxTimed;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev0[h->n_timed], st));
     {

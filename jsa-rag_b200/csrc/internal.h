@@ -66,7 +66,15 @@ struct ScanParams {
   uint32_t* top_flag;       // [grid] token of the launch whose samples CTA c has published
   uint64_t* seed_tag;       // [nblk * kNQ] token << 32 | seed image
   const uint32_t* token;    // search token, bumped by prep_queries_kernel
+  // Pair kernel with several pair blocks per launch: the pairs that walk the same tile sequence publish how far
+  // they are and none runs more than a few tiles ahead of the slowest, so a tile is still in the L2 when its other
+  // readers ask for it (without this the siblings drift apart and DRAM delivers every tile 1.5 - 2.5 times).
+  unsigned long long* progress;   // [grid / 2] (tag << 32 | tiles issued) per CTA pair; NULL = no lock-step
+  int scan_seq;                   // number of this scan launch within the search (tag = token * 4096 + scan_seq)
+  int lock_window;                // tiles a pair may be ahead of its slowest sibling
 };
+constexpr int kLockWindow = 8;    // default window (JSA_MIPS_LOCK_WINDOW overrides)
+constexpr int kLockEvery = 4;     // the siblings' progress is looked at every this many tiles
 constexpr int kTopJ = 4;
 constexpr int kSeedSlots = 5;   // a lane of the selecting warp looks after CTAs lane, lane + 32, ... (5 * 32 = 160 >= 148)
 
@@ -78,6 +86,7 @@ constexpr int kDbgOneBlock = 32;  // one query block per launch even for large b
 constexpr int kDbgHostPrepass = 64; // seed thresholds with separate sampled scan + select launches (the pre-fusion path; always used for k > 128)
 constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
 constexpr int kDbgNoTma = 256;   // the producer hands over stages without loading them (power/latency split; results meaningless)
+constexpr int kDbgNoLockstep = 512;  // pairs sharing a tile sequence run free (A/B test of the L2 lock-step)
 constexpr int kDbgNoPair = 128;  // batches > 128 without tcgen05 CTA pairs (the round-1 multi-block path; A/B test)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kNumStats };

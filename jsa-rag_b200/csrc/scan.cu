@@ -324,8 +324,37 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
+    // lock-step of the pairs that share this tile sequence (see ScanParams::progress)
+    bool lockstep = kPair && leader && p.progress != nullptr && p.nblk > 2;
+    const int npb = p.nblk >> 1, my_pair = static_cast<int>(blockIdx.x >> 1);
+    const int group0 = npb > 0 ? (my_pair / npb) * npb : 0;
+    unsigned long long tag = 0;
+    if (lockstep) {
+      ptx::griddep_wait();   // the search token is bumped by the query-preparation kernel of this search
+      tag = static_cast<unsigned long long>(*reinterpret_cast<const volatile uint32_t*>(p.token) * 4096u +
+                                            static_cast<uint32_t>(p.scan_seq)) << 32;
+    }
     for (int i = 0; i < n_iter; ++i) {
       const int t = first_tile + (i < n_samp ? i : i - n_samp) * tile_step;
+      if (lockstep && i >= p.lock_window && (i % kLockEvery) == 0) {
+        if (lane == 0) {
+          const unsigned long long need = tag | static_cast<unsigned long long>(i - p.lock_window);
+          for (int sblg = 0; sblg < npb && lockstep; ++sblg) {
+            if (group0 + sblg == my_pair) continue;
+            const unsigned long long* slot = p.progress + group0 + sblg;
+            int polls = 0;
+            // a sibling that carries another tag has not started this launch yet; one that never shows up (its SMs
+            // are busy with another kernel) must not stall the scan: give up on the lock-step after ~20k polls
+            for (;;) {
+              const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(slot);
+              if ((v >> 32) == (tag >> 32) && v >= need) break;
+              if (++polls > 20000) { lockstep = false; break; }
+              __nanosleep(200);
+            }
+          }
+        }
+        lockstep = __shfl_sync(0xffffffffu, lockstep ? 1 : 0, 0) != 0;
+      }
       for (int si = 0; si < stages_per_tile; ++si) {
         const long long w0 = want_stats ? clock64() : 0;
         ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
@@ -360,6 +389,8 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      if (kPair && leader && p.progress != nullptr && p.nblk > 2 && lane == 0)
+        *reinterpret_cast<volatile unsigned long long*>(p.progress + my_pair) = tag | static_cast<unsigned long long>(i);
     }
     if (want_stats && lane == 0) my_stats[kStProdWait] = st_a;
   } else if (warp == 1) {

@@ -81,19 +81,20 @@ from fastapi.testclient import TestClient
 holder = eng.IndexHolder(server)
 client = TestClient(eng.create_app(holder))
 payload = {"query_embs": q.reshape(-1).tolist(), "bsz": B, "topk": K}
-body32 = q.numpy().astype("<f4").tobytes()
+body_json = json.dumps(payload).encode()        # what the reference client sends (src/post.py:10-28), encoded once:
+body32 = q.numpy().astype("<f4").tobytes()      # the timings below are the server's side of a request
 
 
 def http_json():
-    r = client.post("/retrieve", json=payload)
+    r = client.post("/retrieve", content=body_json, headers={"content-type": "application/json"})
     assert r.status_code == 200
-    return r.json()
+    return r
 
 
 def http_bin():
     r = client.post(f"/retrieve_bin?bsz={B}&topk={K}&dtype=fp32", content=body32)
     assert r.status_code == 200
-    return r.json()
+    return r
 
 
 def http_search_bin():
@@ -105,7 +106,9 @@ def http_search_bin():
 out["POST /retrieve (reference JSON)"] = timeit(http_json, max(5, iters // 3))
 out["POST /retrieve_bin"] = timeit(http_bin, max(5, iters // 3))
 out["POST /search_bin"] = timeit(http_search_bin, iters)
-docs, scores = http_json()
+docs, scores = http_json().json()
+out["request_bytes"] = {"json": len(body_json), "binary": len(body32)}
+out["response_bytes"] = {"json": len(http_json().content), "search_bin": len(http_search_bin())}
 raw = http_search_bin()
 ids = np.frombuffer(raw[B * K * 4:], dtype="<i8").reshape(B, K)
 ds, di = server.search(q, K)

@@ -190,6 +190,22 @@ def rerank_tail(query_emb: torch.Tensor, passage_emb: torch.Tensor, topk: int):
 
 
 # --------------------------------------------------------------------------------------------
+# src/index.py:195-223 — DistributedFAISSIndex with faiss_index_type="flat" 
+# --------------------------------------------------------------------------------------------
+def faiss_flat_search(queries: torch.Tensor, embeddings_dn_fp16: torch.Tensor, topk: int
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GpuIndexFlatIP over ``_cast_to_torch32(self.embeddings.T)`` searched with ``_cast_to_torch32(allqueries)``,
+    scores cast ``.half()`` (src/index.py:205,217,223).  The stored matrix is the fp16 one of init_embeddings
+    (src/index.py:52, inherited), so the vectors faiss holds are fp32 copies of fp16-rounded values; the QUERIES stay
+    fp32 (the flat DistributedIndex rounds them to fp16, :118) and the products are accumulated in fp32.
+    faiss-gpu 1.7.2 is not installed here: PARITY UNPINNED — this restates the documented semantics of IndexFlatIP
+    (exact inner products, larger first)."""
+    s = queries.float() @ embeddings_dn_fp16.float()
+    top, idx = torch.topk(s, topk, dim=1)
+    return top.half(), idx
+
+
+# --------------------------------------------------------------------------------------------
 # build_server/server_start.py:139-163 — faiss server search (normalise queries, exact IP)
 # --------------------------------------------------------------------------------------------
 def normalize_l2(x: np.ndarray) -> np.ndarray:

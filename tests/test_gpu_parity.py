@@ -593,6 +593,27 @@ def test_handles_of_different_dims_share_a_device(eng, dev):
         assert torch.equal(i, ri)
 
 
+def test_faiss_flat_mode_matches_its_restatement(eng, dev, tmp_path):
+    """index_mode="faiss", faiss_index_type="flat" (src/index.py:164-223) runs on the same engine: against
+    the restated faiss semantics (fp32 queries over the fp16-stored matrix, scores .half()) the answer stays inside
+    north_star's tolerance (1e-3 relative) — the only arithmetic difference is the fp16 rounding of the queries."""
+    class Opt:
+        index_mode, faiss_index_type, faiss_code_size = "faiss", "flat", None
+        retriever_model_path, load_index_path, passages, max_passages = "facebook/contriever", None, [], -1
+    index, _ = eng.load_or_initialize_index(Opt())
+    n, k = 80_000, 100
+    e, q = _synth(n, 768, 48, 3, dev)
+    index.init_embeddings([{"id": str(i)} for i in range(n)], dim=768)
+    index.embeddings[:, :] = e.T
+    docs, scores = index.search_knn(q, k)
+    ids = np.array([[int(d["id"]) for d in row] for row in docs])
+    e_dn = O.make_embeddings_dn(e.cpu())
+    fs, fi = O.faiss_flat_search(q.cpu(), e_dn, k)
+    exact = O.exact_scores(q.cpu().numpy(), e.cpu().numpy(), q_dtype=np.float32)
+    rep = O.compare_topk(ids, np.array(scores), fi.numpy(), fs.float().numpy(), exact, rtol=RTOL)
+    assert rep["ok"], rep["errors"][:3]
+
+
 def test_randomised_configurations(eng, dev):
     """Seeded random mix of shapes, dtypes, layouts, id mappings and k (interactions between the small /
     big-k modes, M=64 / M=128 / multi-block launches, the smem K tail of dim 1024 and both layouts)."""

@@ -114,3 +114,22 @@ def test_oracle_against_live_reference():
     exact = O.exact_scores(q, e16)
     assert O.compare_topk(i.numpy(), s.float().numpy(), ids, scores, exact)["ok"]
     assert idx.search_knn(torch.from_numpy(q[:0]), 5) == ([], [])
+
+
+def test_faiss_flat_mode_is_within_tolerance_of_the_flat_index():
+    """index_mode="faiss", faiss_index_type="flat" is served by the same engine.  The reference's faiss
+    flat path differs from its torch flat path only in keeping the QUERIES in fp32 (src/index.py:217 vs :118); on
+    unit-norm Contriever-shaped vectors that moves a top-k score by < 1e-3 relative (north_star's tolerance), and the
+    `.half()` both paths apply to the returned scores (:223 / :118) rounds by up to 4.9e-4 on its own."""
+    g = torch.Generator().manual_seed(11)
+    e = torch.nn.functional.normalize(torch.randn(60_000, 768, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(32, 768, generator=g), dim=1)
+    e_dn = O.make_embeddings_dn(e)
+    fs, fi = O.faiss_flat_search(q, e_dn, 100)
+    ts, ti = O.compute_scores_and_indices(q, e_dn, 100)
+    exact = O.exact_scores(q.numpy(), e_dn.T.contiguous().numpy(), q_dtype=np.float32)     # fp32 queries, fp16-stored rows
+    rep = O.compare_topk(ti.numpy(), ts.float().numpy(), fi.numpy(), fs.float().numpy(), exact, rtol=1e-3)
+    assert rep["ok"], rep["errors"][:3]
+    unrounded = torch.gather(q @ e_dn.float(), 1, fi)
+    rel = ((fs.float() - unrounded).abs() / unrounded.abs()).max().item()
+    assert rel <= 2 ** -11 * 1.001                                                          # fp16 output rounding: half an ulp

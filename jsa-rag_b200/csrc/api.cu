@@ -156,7 +156,7 @@ WsLayout ws_layout(const mips_handle* h, int max_batch, int max_k) {
   w.pk_off = off;   off += align_up(grid * kNQ * sizeof(int), 1024);
   w.seed_s_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * max_k * sizeof(float), 1024);
   w.seed_i_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * max_k * sizeof(int64_t), 1024);
-  w.top_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * grid * kTopJ * sizeof(uint32_t), 1024);
+  w.top_off = off; off += align_up(static_cast<size_t>(kMaxQBlocks * kNQ) * grid * kTopJPair * sizeof(uint32_t), 1024);
   w.total = off;
   return w;
 }
@@ -405,9 +405,10 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     const bool pair = pairs_ok && rem > kNQ;
     int nblk, launch_grid;
     if (pair) {
-      // pair blocks of this launch: 4 (1024 queries per pass over the index) halve the HBM/L2 traffic per flop
-      // once more, at the price of 2 idle pairs of 74 (72 = 4 x 18 tile sequences)
-      static const int max_npb = []() { const char* e = getenv("JSA_MIPS_PAIR_BLOCKS"); const int v = e ? atoi(e) : 4; return v == 4 ? 4 : (v == 1 ? 1 : 2); }();
+      // pair blocks of this launch: 1 or 2.  (4 blocks = 1024 queries per pass over the index, JSA_MIPS_PAIR_BLOCKS=4,
+      // halve the HBM traffic once more but leave 2 of 74 pairs idle and keep four pairs in lock-step: measured
+      // +2 % on one GPU at 33M rows, -7 % on the shards of 2-8 GPUs, so two launches of 2 blocks are the default)
+      static const int max_npb = []() { const char* e = getenv("JSA_MIPS_PAIR_BLOCKS"); const int v = e ? atoi(e) : 2; return v == 4 ? 4 : (v == 1 ? 1 : 2); }();
       int npb = rem > 4 * kNQ && max_npb >= 4 ? 4 : (rem > 2 * kNQ && max_npb >= 2 ? 2 : 1);
       nblk = 2 * npb;
       int pairs = grid / 2 < h->max_pairs ? grid / 2 : h->max_pairs;
@@ -469,8 +470,8 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     // and 4x more per-CTA values than k: with fewer (large batches split the CTAs over 2-4 query blocks) the top-kTopJ
     // truncation loosens the seed and the separate sampled launches win (measured at batch 1024: 48.3 vs 49.5 ms).
     p.sample_tiles = 0;
-    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) && nslots * kTopJ >= 4 * k &&
-        nslots <= 32 * kSeedSlots && launch_grid * 4 >= p.batch && launch_grid * sizeof(uint32_t) <= kSyncSeedOff &&
+    if (n_levels > 0 && k <= kSmallK && !(h->dbg_flags & kDbgHostPrepass) &&
+        nslots * (pair ? kTopJPair : kTopJ) >= 4 * k && nslots <= 32 * (pair ? kSeedSlotsPair : kSeedSlots) && launch_grid * 4 >= p.batch && launch_grid * sizeof(uint32_t) <= kSyncSeedOff &&
         n_launch < 64) {
       p.sample_tiles = levels[n_levels - 1];
       p.launch_idx = n_launch;

@@ -62,7 +62,7 @@ struct ScanParams {
   // full scan starts with that threshold.  0 = off (the thresholds come from `seed` or start at -inf).
   int sample_tiles;
   int launch_idx;           // scan launch number within the search (token = search token * 64 + launch_idx)
-  uint32_t* top;            // [nblk * kNQ][grid / nblk][kTopJ] orderable score images (nblk <= kMaxQBlocks)
+  uint32_t* top;            // [nblk * kNQ][grid / nblk][kTopJ or kTopJPair] orderable score images (nblk <= kMaxQBlocks)
   uint32_t* top_flag;       // [grid] token of the launch whose samples CTA c has published
   uint64_t* seed_tag;       // [nblk * kNQ] token << 32 | seed image
   const uint32_t* token;    // search token, bumped by prep_queries_kernel
@@ -77,6 +77,8 @@ constexpr int kLockWindow = 8;    // default window (JSA_MIPS_LOCK_WINDOW overri
 constexpr int kLockEvery = 4;     // the siblings' progress is looked at every this many tiles
 constexpr int kTopJ = 4;
 constexpr int kSeedSlots = 5;   // a lane of the selecting warp looks after CTAs lane, lane + 32, ... (5 * 32 = 160 >= 148)
+constexpr int kTopJPair = 16;   // pair kernel: 37 or 74 lists per query block, hence deeper per-CTA samples
+constexpr int kSeedSlotsPair = 3;   // 3 * 32 = 96 >= 74 pairs
 
 constexpr int kDbgNoSelect = 1;  // epilogue only drains TMEM (isolates GEMM + streaming)
 constexpr int kDbgNoMma = 2;     // no tcgen05.mma, stages are released immediately (isolates TMA streaming)

@@ -229,6 +229,8 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
   const int nk_ss = nk - nk_ts;                               // ... and in shared memory (dim > 768)
   const int S = p.num_stages;
   const int cps = p.chunks_per_stage;                            // K chunks one pipeline stage carries
+  constexpr int kJ = kPair ? kTopJPair : kTopJ;                  // sampled-seeding values per (CTA, query)
+  constexpr int kSlots = kPair ? kSeedSlotsPair : kSeedSlots;    // ... and lists a lane of the selecting warp covers
   constexpr int kBoxRows = kPair ? kTileN / 2 : kTileN;          // passage rows this CTA loads per tile
   constexpr int kBoxBytes = kBoxRows * kKChunk * 2;              // one K chunk of them (SWIZZLE_128B)
   const int stage_bytes = cps * kBoxBytes;
@@ -534,8 +536,13 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
     int it = 0;
 
     if (p.sample_tiles > 0) {
-      // ---- phase A: the kTopJ best scores of my query over this CTA's sample tiles (registers only) ----
-      float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+      // ---- phase A: the kJ best scores of my query over this CTA's sample tiles (registers only) ----
+      // kJ = 4 when 148 single CTAs sample for a query block, 16 in the pair kernel, where only 37 (or 74) CTAs
+      // do: the k-th best of the union of per-CTA top-kJ lists is only a tight bound while a CTA rarely holds
+      // more than kJ of the sample's top k.
+      float tj[kJ];
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) tj[j] = -INFINITY;
       for (; it < n_samp; ++it) {
         const int buf = it & 1;
         ptx::mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
@@ -551,10 +558,10 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
         uint32_t pm0 = 0, pm1 = 0;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (__uint_as_float(r0[c]) > t3) pm0 |= 1u << c;
+          if (__uint_as_float(r0[c]) > tj[kJ - 1]) pm0 |= 1u << c;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (__uint_as_float(r1[c]) > t3) pm1 |= 1u << c;
+          if (__uint_as_float(r1[c]) > tj[kJ - 1]) pm1 |= 1u << c;
         const int64_t nvalid = p.n_local - static_cast<int64_t>(first_tile + it * tile_step) * kTileN;
         if (nvalid < kTileN) {
           const uint64_t vm = (1ull << nvalid) - 1ull;
@@ -566,20 +573,21 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
           if (pm0 != 0u) { c = __ffs(pm0) - 1; pm0 &= pm0 - 1u; }
           else { c = 32 + __ffs(pm1) - 1; pm1 &= pm1 - 1u; }
           const float s = __uint_as_float(pick64(r0, r1, c));
-          if (s > t3) {
-            t3 = s;
-            if (t3 > t2) { const float x = t2; t2 = t3; t3 = x; }
-            if (t2 > t1) { const float x = t1; t1 = t2; t2 = x; }
-            if (t1 > t0) { const float x = t0; t0 = t1; t1 = x; }
+          if (s > tj[kJ - 1]) {       // insert into the sorted (descending) list: one bubble pass from the tail
+            tj[kJ - 1] = s;
+#pragma unroll
+            for (int j = kJ - 1; j > 0; --j)
+              if (tj[j] > tj[j - 1]) { const float x = tj[j - 1]; tj[j - 1] = tj[j]; tj[j] = x; }
           }
         }
         __syncwarp();
       }
       const uint32_t token = *reinterpret_cast<const volatile uint32_t*>(p.token) * 64u + static_cast<uint32_t>(p.launch_idx);
       if (lane_ok) {
-        uint4 v;
-        v.x = f32_to_ord(t0); v.y = f32_to_ord(t1); v.z = f32_to_ord(t2); v.w = f32_to_ord(t3);
-        reinterpret_cast<uint4*>(p.top)[static_cast<size_t>(qblk * kNQ + ql) * tile_step + first_tile] = v;
+        uint4* dst = reinterpret_cast<uint4*>(p.top) + (static_cast<size_t>(qblk * kNQ + ql) * tile_step + first_tile) * (kJ / 4);
+#pragma unroll
+        for (int j = 0; j < kJ / 4; ++j)
+          dst[j] = make_uint4(f32_to_ord(tj[4 * j]), f32_to_ord(tj[4 * j + 1]), f32_to_ord(tj[4 * j + 2]), f32_to_ord(tj[4 * j + 3]));
       }
       __threadfence();
       ptx::named_bar_sync(3, 128);
@@ -589,30 +597,33 @@ __device__ __forceinline__ void scan_body(const CUtensorMap& tmap_e, const CUten
         const int qq = static_cast<int>(blockIdx.x) + (warp - 2) * static_cast<int>(gridDim.x);
         if (qq < p.batch) {
           const int qb = qq / kNQ;                           // lists of query block qb come from CTAs s * nblk + qb
-          bool ok[kSeedSlots];
+          bool ok[kSlots];
 #pragma unroll
-          for (int j = 0; j < kSeedSlots; ++j) ok[j] = lane + 32 * j >= tile_step;   // slots that do not exist count as done
+          for (int j = 0; j < kSlots; ++j) ok[j] = lane + 32 * j >= tile_step;   // slots that do not exist count as done
           for (int spins = 0; spins < kSeedOwnerSpins; ++spins) {
             bool all = true;
 #pragma unroll
-            for (int j = 0; j < kSeedSlots; ++j) {
+            for (int j = 0; j < kSlots; ++j) {
               if (!ok[j]) ok[j] = ld_acquire_u32(p.top_flag + (lane + 32 * j) * p.nblk + qb) == token;
               all = all && ok[j];
             }
             if (__all_sync(0xffffffffu, all)) break;
             __nanosleep(100);
           }
-          const uint4* src = reinterpret_cast<const uint4*>(p.top) + static_cast<size_t>(qq) * tile_step;
+          const uint4* src = reinterpret_cast<const uint4*>(p.top) + static_cast<size_t>(qq) * tile_step * (kJ / 4);
           const uint32_t absent = f32_to_ord(-INFINITY);    // a CTA that did not make it contributes -inf
-          uint32_t v[kSeedSlots * kTopJ];
+          uint32_t v[kSlots * kJ];
 #pragma unroll
-          for (int j = 0; j < kSeedSlots; ++j) {
+          for (int j = 0; j < kSlots; ++j) {
             const int slot = lane + 32 * j;
-            uint4 x = make_uint4(0u, 0u, 0u, 0u);               // 0 = not a candidate
-            if (slot < tile_step) x = ok[j] ? __ldcg(src + slot) : make_uint4(absent, absent, absent, absent);
-            v[4 * j + 0] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+#pragma unroll
+            for (int u = 0; u < kJ / 4; ++u) {
+              uint4 x = make_uint4(0u, 0u, 0u, 0u);               // 0 = not a candidate
+              if (slot < tile_step) x = ok[j] ? __ldcg(src + static_cast<size_t>(slot) * (kJ / 4) + u) : make_uint4(absent, absent, absent, absent);
+              v[kJ * j + 4 * u + 0] = x.x; v[kJ * j + 4 * u + 1] = x.y; v[kJ * j + 4 * u + 2] = x.z; v[kJ * j + 4 * u + 3] = x.w;
+            }
           }
-          const uint32_t kth = warp_kth_largest<kSeedSlots * kTopJ>(v, p.k);
+          const uint32_t kth = warp_kth_largest<kSlots * kJ>(v, p.k);
           if (lane == 0) st_release_u64(p.seed_tag + qq, (static_cast<uint64_t>(token) << 32) | kth);
         }
       }

@@ -69,6 +69,14 @@ class PassageStore:
         root = dist_utils.all_gather_object(root)[0]
         ok = True
         try:
+            # cheap feasibility check before serialising millions of records: the node-local directory must hold
+            # every rank's shard (sizes estimated from the first records of this shard)
+            probe = min(n_local, 512)
+            if probe:
+                avg = sum(len(pickle.dumps(local_passages[i], protocol=pickle.HIGHEST_PROTOCOL)) for i in range(probe)) / probe
+                need = int((avg + 8) * n_local * 1.1) * w
+                if shutil.disk_usage(root).free < need:
+                    raise OSError(f"{root}: {need} bytes needed for the shared passage store")
             blob, offs = cls.serialise(local_passages, n_local)
             with open(os.path.join(root, f"passages.{r}.bin"), "wb") as f:
                 f.write(blob if blob else b"\0")        # an empty file cannot be mapped

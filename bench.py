@@ -544,8 +544,9 @@ def run_b200(args):
                 "metric": METRIC, "value": args.batch * sps * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
-                "config": dict(workload(args, world), **({"exchange": "nvlink peer stores (queries and candidates) + wait-and-merge kernel" if p2p
-                                                          else "nccl all-gather + merge kernel"} if world > 1 else {})),
+                "config": workload(args, world),       # identical to the reference arm's config object
+                "exchange": (("nvlink peer stores (queries and candidates) + wait-and-merge kernel" if p2p
+                              else "nccl all-gather + merge kernel") if world > 1 else None),
                 "e2e": {"value": args.batch * sps * args.steps / e2e_s, "unit": UNIT,
                         "path": "mips_search_host (C ABI, host buffers)" if world == 1 else
                                 ("B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)"

@@ -514,6 +514,29 @@ def test_concurrent_searches_on_two_streams(eng, dev):
         assert torch.equal(i, ri) and torch.equal(s, rs)
 
 
+def test_concurrent_pair_scans_on_two_streams(eng, dev):
+    """The same with the CTA-pair kernel (clusters of 2, two pair blocks per launch): pairs that share a tile sequence
+    keep in lock-step through progress words, and a sibling whose SMs are held by the other stream's kernel must only
+    cost a bounded wait (the lock-step is dropped), never a hang or a wrong answer."""
+    e1, q1 = _synth(700_000, 768, 512, 81, dev)
+    e2, q2 = _synth(600_000, 768, 300, 82, dev)
+    m1, m2 = _engine(eng, e1), _engine(eng, e2)
+    ref1, ref2 = m1.search(q1, 100), m2.search(q2, 20)
+    ref1, ref2 = tuple(t.clone() for t in ref1), tuple(t.clone() for t in ref2)
+    torch.cuda.synchronize()
+    st1, st2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    outs = []
+    for _ in range(6):
+        with torch.cuda.stream(st1):
+            outs.append((0, m1.search(q1, 100)))
+        with torch.cuda.stream(st2):
+            outs.append((1, m2.search(q2, 20)))
+    torch.cuda.synchronize()
+    for which, (s, i) in outs:
+        rs, ri = (ref1, ref2)[which]
+        assert torch.equal(i, ri) and torch.equal(s, rs)
+
+
 @pytest.mark.parametrize("k", [100, 700])
 def test_adversarial_row_order(eng, dev, k):
     """Scores that grow with the row number defeat the seeded thresholds (the sample is the worst part

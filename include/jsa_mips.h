@@ -224,10 +224,13 @@ int mips_last_launch_count(const mips_handle* h);
  * MMAs (pure TMA streaming) — results are meaningless with either set; 4 = no sampled pre-pass;
  * 8 = time the scan launches; 16 = always UMMA M=128; 32 = one query block per launch; 64 = seed the thresholds
  * with separate sampled scan + select launches instead of inside the scan kernel; 128 = batches > 128 without
- * tcgen05 CTA pairs (the round-1 multi-block path).  stats_dev: device array of
+ * tcgen05 CTA pairs (the round-1 multi-block path); 256 = the producer hands stages over without loading them
+ * (results meaningless: power / latency split); 512 = CTA pairs that share a tile sequence run without the L2
+ * lock-step.  Environment switches read once per process: JSA_MIPS_PDL=0 (no programmatic dependent launch),
+ * JSA_MIPS_PAIRS=0, JSA_MIPS_PAIR_BLOCKS=1|2|4, JSA_MIPS_LOCK_WINDOW=<tiles>, JSA_MIPS_NVTX=1.  stats_dev: device array of
  * [mips_num_sms()][mips_debug_num_stats()] uint64 per-CTA cycle counters the scan kernel fills
  * (caller zeroes it), or NULL.  Counter order: producer wait, MMA wait(full), MMA wait(TMEM),
- * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles.
+ * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles, epilogue tcgen05.ld.
  */
 int mips_debug_config(mips_handle* h, int flags, void* stats_dev);
 /* With flag 8 set, every full-shard scan launch is bracketed by CUDA events on the caller's stream;

@@ -18,6 +18,10 @@
 //    (exact bisection select, no sort) and raises the threshold.
 // The per-CTA lists are reduced by select_topk_kernel (merge.cu).
 //
+// Three instances of one body: mips_scan_kernel ([n, dim] storage, <= 128 queries per CTA), mips_scan_dn_kernel
+// ([dim, n] storage, MN-major B operand) and mips_scan_pair_kernel (batches > 128: the two CTAs of a cluster form a
+// tcgen05 CTA pair, UMMA M = 256, each CTA loads half of every passage tile; see scan_body).
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue/select (TMEM lane quarter = warp_id % 4).
 #include "internal.h"

@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-api-e2e", action="store_true")
+    ap.add_argument("--replicated-queries", action="store_true",
+                    help="N > 1: every rank passes the same batch (a front end broadcasting a request to the shards) instead "
+                         "of batch/N queries each; implied when the batch does not divide by N")
     ap.add_argument("--sweep", default="", help="comma list of batch[:k[:searches_per_step]] measured over ONE resident index, "
                                                 "one JSON line each (BASELINE configs[2..4]); default: the single headline config")
     return ap.parse_args()
@@ -56,7 +59,9 @@ def workload(args, world):
             "rows": args.rows, "dim": args.dim, "batch": args.batch, "k": args.k,
             "sharding": "single shard" if world == 1 else f"round-robin rows over {world} ranks",
             "l2": "index pass (rows*dim*2 bytes per rank) exceeds the 126 MB L2; no flush needed",
-            "queries_per_rank": args.batch // world, "searches_per_step": args.searches_per_step}
+            "queries_per_rank": (args.batch // world if args.batch % world == 0 and not getattr(args, "replicated_queries", False)
+                                 else f"{args.batch} (the same queries on every rank)"),
+            "searches_per_step": args.searches_per_step}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -209,7 +214,7 @@ class PooledDocMap:
         return tab[np.arange(self.n, dtype=np.int64) & (len(self.pool) - 1)]
 
 
-def parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets):
+def parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets, repl=False):
     """Correctness evidence carried by the bench line (outside every timed region): the searches that were timed are
     checked against planted nearest neighbours on the full index, against the NCCL all-gather + merge path bit for
     bit (N > 1), and against the reference arithmetic (oracle, CPU) on a sub-shard with oracle.compare_topk."""
@@ -228,20 +233,23 @@ def parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets):
     rows = torch.randint(0, n_loc, (per,), generator=g, device=dev)
     qp = index._store[rows].float()
     qp = torch.nn.functional.normalize(qp + 0.02 * torch.randn(qp.shape, generator=g, device=dev) / (args.dim ** 0.5), dim=1)
-    s, i = index.search(qp, k)
     want = index._id_base + rows * index._id_stride
+    if repl:                                   # the same queries on every rank: rank 0's plants
+        dist.broadcast(qp, 0)
+        dist.broadcast(want, 0)
+    s, i = index.search(qp, k, replicated=repl)
     planted_ok = bool((i[:, 0] == want).all()) and bool((s[:, 0] > 0.99).all()) and bool((s[:, 1:] <= s[:, :-1]).all())
     checked.append("planted nearest neighbours (full index, every rank's queries)")
     ok = ok and planted_ok
 
     # ---- (2) peer-exchange path == NCCL all-gather + merge path, bit for bit
     if world > 1:
-        ref_s, ref_i = index.search(q_sets[0], k)
+        ref_s, ref_i = index.search(q_sets[0], k, replicated=repl)
         ref_s, ref_i = ref_s.clone(), ref_i.clone()
         saved = (getattr(index, "_xchg", None), getattr(index, "_xchg_q", None))
         if saved[0]:
             index._xchg, index._xchg_q = False, False
-            n_s, n_i = index.search(q_sets[0], k)
+            n_s, n_i = index.search(q_sets[0], k, replicated=repl)
             index._xchg, index._xchg_q = saved
             same = torch.equal(n_s, ref_s) and torch.equal(n_i, ref_i)
             checked.append("nvlink peer exchange == nccl all-gather + merge (bit-identical scores and ids)")
@@ -260,14 +268,17 @@ def parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets):
     sub._store = index._store[:sub_n]
     sub._set_sharding("round_robin")
     sub.equal_batch = index.equal_batch
-    ss, si = sub.search(q_sets[0], k)
+    ss, si = sub.search(q_sets[0], k, replicated=repl)
     if world > 1:
         all_e = torch.empty((world, sub_n, args.dim), dtype=tdtype, device=dev)
         dist.all_gather_into_tensor(all_e, sub._store.contiguous())
-        sizes = eng.dist_utils.get_varsize(ss)
-        ss = eng.dist_utils.varsize_all_gather(ss.contiguous(), sizes)      # rank order = query order
-        si = eng.dist_utils.varsize_all_gather(si.contiguous(), sizes)
-        qq = eng.dist_utils.varsize_all_gather(q_sets[0].contiguous(), sizes)
+        if repl:
+            qq = q_sets[0]                                                   # every rank already holds all rows
+        else:
+            sizes = eng.dist_utils.get_varsize(ss)
+            ss = eng.dist_utils.varsize_all_gather(ss.contiguous(), sizes)      # rank order = query order
+            si = eng.dist_utils.varsize_all_gather(si.contiguous(), sizes)
+            qq = eng.dist_utils.varsize_all_gather(q_sets[0].contiguous(), sizes)
         emb = all_e.permute(1, 0, 2).reshape(sub_n * world, args.dim)     # global id = local * W + rank
         sub.close_exchange()
     else:
@@ -329,15 +340,18 @@ def run_b200(args):
     del c
     def measure(args, first):
         sps = max(1, args.searches_per_step)
-        sizes = [args.batch // world + (1 if r < args.batch % world else 0) for r in range(world)]
-        offs = [sum(sizes[:r]) for r in range(world + 1)]
+        # every rank contributes batch/N queries (reference training flow); a batch that does not divide by N is
+        # searched the way a serving front end would: the same queries on every rank, no query exchange
+        repl = world > 1 and (args.replicated_queries or args.batch % world != 0)
+        sizes = [args.batch] * world if repl else [args.batch // world] * world
+        offs = [0] * (world + 1) if repl else [sum(sizes[:r]) for r in range(world + 1)]
         per = sizes[rank]
-        index.equal_batch = args.batch % world == 0   # every rank contributes batch/N queries (else sizes are exchanged)
+        index.equal_batch = True
         q_sets, q_hosts = [], []
         for j in range(sps):     # one query set per search of a step (posterior / prior queries differ)
             q_all = torch.nn.functional.normalize(torch.randn(args.batch, args.dim, device=dev,
                                                               generator=torch.Generator(device=dev).manual_seed(4321 + j)), dim=1)
-            q_mine = q_all[offs[rank]:offs[rank + 1]].contiguous() if world > 1 else q_all
+            q_mine = q_all[offs[rank]:offs[rank + 1]].contiguous() if (world > 1 and not repl) else q_all
             q_sets.append(q_mine)
             q_hosts.append(q_mine.cpu().pin_memory())
 
@@ -347,7 +361,7 @@ def run_b200(args):
 
         def step():
             for q in q_sets:
-                out = index.search(q, args.k)
+                out = index.search(q, args.k, replicated=repl)
             return out
 
         def sync_all():
@@ -429,7 +443,7 @@ def run_b200(args):
             # graph of the same public search (collectives included); fall back to the eager call if capture fails
             okf = torch.ones(1, device=dev)
             try:
-                graphed = index.make_graphed_search(per, args.k)
+                graphed = index.make_graphed_search(per, args.k, replicated=repl)
             except Exception as ex:  # noqa: BLE001
                 okf.zero_()
                 sys.stderr.write(f"[rank {rank}] CUDA-graph capture unavailable, eager e2e path: {ex}\n")
@@ -447,7 +461,7 @@ def run_b200(args):
                     if graphed is not None:
                         s, i = graphed(qh)
                     else:
-                        s, i = index.search(qh.to(dev, non_blocking=True), args.k)
+                        s, i = index.search(qh.to(dev, non_blocking=True), args.k, replicated=repl)
                     res_s.copy_(s, non_blocking=True); res_i.copy_(i, non_blocking=True)
                     torch.cuda.current_stream().synchronize()
 
@@ -466,7 +480,7 @@ def run_b200(args):
 
         # ---- the reference-facing call itself: search_knn -> (docs, scores) as nested Python lists ----
         api = None
-        if not args.no_api_e2e:
+        if not args.no_api_e2e and not repl:      # search_knn is the per-rank-queries call of the reference
             if not isinstance(index.doc_map, PooledDocMap):
                 index.doc_map = PooledDocMap(n_loc)
                 index.refresh_passages()
@@ -492,7 +506,7 @@ def run_b200(args):
                            "dicts for the k winners of this rank's queries + fp16-rounded score lists",
                    "passages": getattr(index, "last_passage_path", None)}
 
-        parity = None if args.no_parity else parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets)
+        parity = None if args.no_parity else parity_checks(eng, index, args, world, rank, dev, tdtype, q_sets, repl)
 
         if rank == 0:
             peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -551,8 +565,8 @@ def run_b200(args):
                         "path": "mips_search_host (C ABI, host buffers)" if world == 1 else
                                 ("B200Index.make_graphed_search (CUDA-graph replay of the public distributed search)"
                                  if graphed_used else "B200Index.search (public distributed API, eager)"),
-                        "h2d_bytes_per_step": int(args.batch * args.dim * 4 * sps),
-                        "d2h_bytes_per_step": int(args.batch * args.k * 12 * sps)},
+                        "h2d_bytes_per_step": int(args.batch * args.dim * 4 * sps * (world if repl else 1)),
+                        "d2h_bytes_per_step": int(args.batch * args.k * 12 * sps * (world if repl else 1))},
                 "api_e2e": api,
                 "gpu_launches": launches * args.steps,
                 "clocks": clocks,

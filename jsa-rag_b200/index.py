@@ -232,12 +232,17 @@ class B200Index(object):
         return merge_topk(scores, ids, topk)
 
     @torch.no_grad()
-    def search(self, queries: torch.Tensor, topk: int, normalize: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search(self, queries: torch.Tensor, topk: int, normalize: bool = False, replicated: bool = False
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Tensor-native distributed search: this rank's queries -> (scores fp32 [b,k], global ids [b,k]).
 
         All ranks must call it together (like the reference's search_knn).  Steps: all-gather
         queries -> local fused search -> exchange of candidates -> device merge -> own rows.  On one node
         both exchanges are NVLink peer stores (exchange.py); otherwise NCCL all-gathers.
+
+        ``replicated=True``: every rank passes the SAME [B, dim] queries (a front end that broadcasts a request to
+        the shards, SURVEY §8e "in the server/benchmark the same [B, D] is broadcast"): there is no query exchange
+        and every rank receives the merged result of all B queries.
         """
         w, r = dist_utils.get_world_size(), dist_utils.get_rank()
         self._any_rank_has_queries = False
@@ -252,10 +257,14 @@ class B200Index(object):
             # the reference fails inside torch.topk on the rank whose shard is too small (and leaves the
             # others waiting in a collective); here every rank raises the same error before communicating
             raise RuntimeError("selected index k out of range")
-        sizes = [int(queries.shape[0])] * w if self.equal_batch else dist_utils.get_varsize(queries)   # src/index.py:129
-        allqueries = None
+        if replicated:
+            sizes = [int(queries.shape[0])] + [0] * (w - 1)      # one logical owner; every rank returns all rows
+            allqueries = queries
+        else:
+            sizes = [int(queries.shape[0])] * w if self.equal_batch else dist_utils.get_varsize(queries)   # src/index.py:129
+            allqueries = None
         nbytes = queries.numel() * queries.element_size()
-        if queries.is_cuda and sizes[0] > 0 and len(set(sizes)) == 1 and nbytes % 8 == 0 and queries.dim() == 2 \
+        if allqueries is None and queries.is_cuda and sizes[0] > 0 and len(set(sizes)) == 1 and nbytes % 8 == 0 and queries.dim() == 2 \
                 and torch.distributed.get_backend() == "nccl":
             xq = self._peer_exchange(nbytes, queries.device, "_xchg_q")
             if xq is not None:                                                     # NVLink peer stores, no collective call
@@ -292,8 +301,10 @@ class B200Index(object):
             ls, li = self._local_search(allqueries, topk, normalize)               # src/index.py:132
             gs, gi = dist_utils.all_gather_candidates(ls, li)                      # replaces :139-142
             ms, mi = self._merge_lists(gs, gi, topk)                               # replaces :143-157
-        sl = slice(int(offs[r]), int(offs[r + 1]))
         self._last_all = (mi, offs)
+        if replicated:
+            return ms, mi
+        sl = slice(int(offs[r]), int(offs[r + 1]))
         return ms[sl], mi[sl]
 
     def _peer_exchange(self, block_bytes: int, device, which: str = "_xchg"):
@@ -332,7 +343,8 @@ class B200Index(object):
             self._pstore.close()
             self._pstore, self._store_epoch = None, None
 
-    def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32):
+    def make_graphed_search(self, batch: int, topk: int, normalize: bool = False, query_dtype=torch.float32,
+                            replicated: bool = False):
         """Captures one search for a fixed per-rank batch into a CUDA graph — on several ranks the whole
         distributed flow (query all-gather, fused scan + select, candidate all-gather, merge; NCCL
         collectives are captured too).  Returns ``run(queries) -> (scores, ids)`` that copies the queries
@@ -357,12 +369,12 @@ class B200Index(object):
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(3):                      # warm-up: workspace growth, NCCL channels, lazy inits
-                self.search(static_q, topk, normalize)
+                self.search(static_q, topk, normalize, replicated=replicated)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out_s, out_i = self.search(static_q, topk, normalize)
+            out_s, out_i = self.search(static_q, topk, normalize, replicated=replicated)
         self.equal_batch = prev_equal
 
         state = {"graph": graph, "out": (out_s, out_i)}

@@ -105,6 +105,16 @@ def main():
     run.release()
     del run, gs, gi
 
+    # replicated queries (a front end broadcasting a request): no query exchange, every rank gets every row
+    rs_, ri_ = index.search(q_all, k, replicated=True)
+    assert torch.equal(ri_, fi) and torch.equal(rs_, fs), "replicated-query search differs from the single-GPU answer"
+    run = index.make_graphed_search(q_all.shape[0], k, replicated=True)
+    gs, gi = run(q_all)
+    torch.cuda.synchronize()
+    assert torch.equal(gi, fi)
+    run.release()
+    del run, gs, gi
+
     # uneven / empty local batches still take part in the collectives
     d4, s4 = index.search_knn(my_q[:0] if rank == world - 1 else my_q, k)
     assert (d4 == [] and s4 == []) if rank == world - 1 else len(d4) == my_q.shape[0]

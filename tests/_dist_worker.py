@@ -97,7 +97,10 @@ def worker(rank, world, port, tmpdir, mode):
             assert index._id_base == (0 if rank == 0 else 502)
 
         install_test_doubles(index)
+        stats = {}
+        index.iter_stats = stats                                  # the trainer's dict (src/rag.py:143,170)
         docs, scores = index.search_knn(my_q, k)
+        assert isinstance(stats["runtime/search"], tuple) and stats["runtime/search"][0] > 0 and stats["runtime/search"][1] == 1
         ids = np.array([[int(d["id"]) for d in row] for row in docs], dtype=np.int64)
         rep = O.compare_topk(ids, np.array(scores, dtype=np.float64), g["ids"][my_rows], g["scores"][my_rows].astype(np.float32),
                              exact[my_rows])

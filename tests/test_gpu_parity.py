@@ -71,7 +71,12 @@ def test_drop_in_search_knn_matches_reference_outputs(eng, dev):
     for a in range(0, n, 256):                                   # write site of src/rag.py:108-121
         chunk = torch.from_numpy(g["embeddings"][a:a + 256]).to(dev)
         idx.embeddings[:, a:a + chunk.shape[0]] = chunk.T
+    iter_stats = {}
+    idx.iter_stats = iter_stats                                                  # src/rag.py:143: the trainer's dict
     docs, scores = idx.search_knn(torch.from_numpy(g["queries"]).to(dev), 20)   # docs first (src/index.py:158)
+    # runtime/search (src/rag.py:170) is CUDA-synchronised here and split into device time and host tail
+    assert set(iter_stats) == {"runtime/search", "runtime/search_device", "runtime/search_host_tail"}
+    assert iter_stats["runtime/search"][0] >= iter_stats["runtime/search_device"][0] > 0 and iter_stats["runtime/search"][1] == 1
     assert len(docs) == 8 and len(docs[0]) == 20 and isinstance(docs[0][0], dict) and isinstance(scores[0][0], float)
     ids = np.array([[int(d["id"]) for d in row] for row in docs])
     exact = O.exact_scores(g["queries"], g["embeddings"])

@@ -38,6 +38,10 @@ class PassageStore:
         self._maps = maps
         self._views = [memoryview(m) if m is not None else None for m in maps]
         self._offsets = offsets
+        # decoded records of recently returned remote passages (popular passages recur from search to search):
+        # bounded, cleared wholesale when full
+        self._cache = {}
+        self._cache_cap = int(os.environ.get("JSA_MIPS_PASSAGE_CACHE", 1 << 18))
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -121,10 +125,18 @@ class PassageStore:
     def get_many(self, owners: np.ndarray, local_rows: np.ndarray) -> list:
         """Flat arrays -> list of passage dicts (same order)."""
         out = []
-        loads = pickle.loads
+        loads, cache, cap = pickle.loads, self._cache, self._cache_cap
+        if len(cache) >= cap:
+            cache.clear()
         for o, l in zip(owners.tolist(), local_rows.tolist()):
-            offs = self._offsets[o]
-            out.append(loads(self._views[o][offs[l]:offs[l + 1]]))
+            key = (o << 40) | l
+            doc = cache.get(key)
+            if doc is None:
+                offs = self._offsets[o]
+                doc = loads(self._views[o][offs[l]:offs[l + 1]])
+                if cap:
+                    cache[key] = doc
+            out.append(doc)
         return out
 
     def close(self) -> None:
@@ -135,3 +147,4 @@ class PassageStore:
             if m is not None:
                 m.close()
         self._maps, self._views, self._offsets = [], [], []
+        self._cache = {}

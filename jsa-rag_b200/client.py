@@ -35,7 +35,6 @@ class RetrieveClient:
         docs, scores = reply.json()[:2]
         return docs, scores
 
-
     def retrieve_binary(self, query_embs: torch.Tensor, topk: int = 10, half: bool = False):
         """POST /retrieve_bin: raw fp32 (or fp16) query bytes instead of a JSON float list."""
         q = query_embs.detach().to(device="cpu", dtype=torch.float16 if half else torch.float32).contiguous()
@@ -47,6 +46,23 @@ class RetrieveClient:
             return None
         docs, scores = reply.json()[:2]
         return docs, scores
+
+    def search_binary(self, query_embs: torch.Tensor, topk: int = 10, half: bool = False):
+        """POST /search_bin: binary both ways — returns (scores fp32 [b, k], passage ids int64 [b, k]) as numpy arrays for
+        callers that hold the passage store themselves (76.8 KB instead of ~0.6 MB of JSON for 64 x 100 results)."""
+        import numpy as np
+        q = query_embs.detach().to(device="cpu", dtype=torch.float16 if half else torch.float32).contiguous()
+        b = int(q.shape[0])
+        url = self.url.rsplit("/", 1)[0] + "/search_bin"
+        reply = self.session.post(url, params={"bsz": b, "topk": int(topk), "dtype": "fp16" if half else "fp32"},
+                                  data=q.numpy().tobytes(), headers={"Content-Type": "application/octet-stream"})
+        if reply.status_code != 200:
+            print(f"请求失败，状态码: {reply.status_code}")
+            return None
+        raw = reply.content
+        scores = np.frombuffer(raw[:b * topk * 4], dtype="<f4").reshape(b, topk)
+        ids = np.frombuffer(raw[b * topk * 4:], dtype="<i8").reshape(b, topk)
+        return scores, ids
 
 
 def call_retrieve_api(query_embs=None, topk=10, url: str = DEFAULT_URL, session=None):

@@ -58,6 +58,16 @@ def test_binary_endpoints(eng):
     q = torch.randn(3, 8)
     r = client.post("/retrieve_bin", params={"bsz": 3, "topk": 4}, content=q.numpy().tobytes())
     assert r.status_code == 200 and holder.get().calls[-1] == ((3, 8), 4) and len(r.json()[0]) == 3
+
+    class _Sess:                                        # requests.Session stand-in over the ASGI test client
+        def post(self, url, params=None, data=None, headers=None, json=None):
+            return client.post(url[url.index("/", 8):], params=params, content=data, headers=headers, json=json)
+    from importlib import import_module
+    rc = import_module("jsa-rag_b200.client").RetrieveClient("http://testserver/retrieve", session=_Sess())
+    s_, i_ = rc.search_binary(q, 4)
+    assert s_.shape == (3, 4) and i_.dtype == np.int64 and i_[0, 0] == 7 and s_[2, 3] == 11.0
+    docs_b, scores_b = rc.retrieve_binary(q, 4)
+    assert len(docs_b) == 3 and len(scores_b[0]) == 4
     r = client.post("/retrieve_bin", params={"bsz": 3, "topk": 4, "dtype": "fp16"}, content=q.half().numpy().tobytes())
     assert r.status_code == 200 and holder.get().calls[-1] == ((3, 8), 4)
     r = client.post("/search_bin", params={"bsz": 3, "topk": 4}, content=q.numpy().tobytes())

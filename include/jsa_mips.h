@@ -226,8 +226,8 @@ int mips_last_launch_count(const mips_handle* h);
  * with separate sampled scan + select launches instead of inside the scan kernel; 128 = batches > 128 without
  * tcgen05 CTA pairs (the round-1 multi-block path); 256 = the producer hands stages over without loading them
  * (results meaningless: power / latency split); 512 = CTA pairs that share a tile sequence run without the L2
- * lock-step.  Environment switches read once per process: JSA_MIPS_PDL=0 (no programmatic dependent launch),
- * JSA_MIPS_PAIRS=0, JSA_MIPS_PAIR_BLOCKS=1|2|4, JSA_MIPS_LOCK_WINDOW=<tiles>, JSA_MIPS_NVTX=1.  stats_dev: device array of
+ * lock-step; 2048 = 4 pair blocks (1024 queries) per launch at any index size (automatic only for >= ~23M rows).  Environment switches read once per process: JSA_MIPS_PDL=0 (no programmatic dependent launch),
+ * JSA_MIPS_PAIRS=0, JSA_MIPS_PAIR_BLOCKS=1|2|4 (0 = automatic), JSA_MIPS_LOCK_WINDOW=<tiles>, JSA_MIPS_NVTX=1.  stats_dev: device array of
  * [mips_num_sms()][mips_debug_num_stats()] uint64 per-CTA cycle counters the scan kernel fills
  * (caller zeroes it), or NULL.  Counter order: producer wait, MMA wait(full), MMA wait(TMEM),
  * epilogue wait(TMEM), epilogue select, epilogue compaction, #compactions, #appends, total cycles, epilogue tcgen05.ld.

@@ -405,13 +405,17 @@ int mips_search_local(mips_handle* h, const void* queries, int q_dtype, int64_t 
     const bool pair = pairs_ok && rem > kNQ;
     int nblk, launch_grid;
     if (pair) {
-      // pair blocks of this launch: 1 or 2.  (4 blocks = 1024 queries per pass over the index, JSA_MIPS_PAIR_BLOCKS=4,
-      // halve the HBM traffic once more but leave 2 of 74 pairs idle and keep four pairs in lock-step: measured
-      // +2 % on one GPU at 33M rows, -7 % on the shards of 2-8 GPUs, so two launches of 2 blocks are the default)
-      static const int max_npb = []() { const char* e = getenv("JSA_MIPS_PAIR_BLOCKS"); const int v = e ? atoi(e) : 2; return v == 4 ? 4 : (v == 1 ? 1 : 2); }();
+      // pair blocks of this launch: 1, 2 or 4.  4 blocks (1024 queries per pass over the index) halve the HBM traffic
+      // once more but leave 2 of 74 pairs idle and keep four pairs in lock-step: measured +2..3 % on one GPU at 33M
+      // rows, -7 % on the shards of 2-8 GPUs.  JSA_MIPS_PAIR_BLOCKS=1|2|4 forces the maximum.
+      // 0 (default) = automatic: 4 blocks only when a tile sequence is long (>= 20k tiles, i.e. >= ~23M rows on a
+      // full device), where the saved HBM power outweighs the stalls
+      static const int env_npb = []() { const char* e = getenv("JSA_MIPS_PAIR_BLOCKS"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 2 || v == 1) ? v : 0; }();
+      int pairs = grid / 2 < h->max_pairs ? grid / 2 : h->max_pairs;
+      const int max_npb = (h->dbg_flags & kDbgFourPairBlocks) ? 4
+                          : (env_npb ? env_npb : ((pairs >= 4 && num_tiles / (pairs / 4) >= 20000) ? 4 : 2));
       int npb = rem > 4 * kNQ && max_npb >= 4 ? 4 : (rem > 2 * kNQ && max_npb >= 2 ? 2 : 1);
       nblk = 2 * npb;
-      int pairs = grid / 2 < h->max_pairs ? grid / 2 : h->max_pairs;
       launch_grid = pairs >= npb ? (pairs / npb) * nblk : nblk;    // tiny indices: surplus pairs just idle
     } else {
       nblk = (rem + kNQ - 1) / kNQ;

@@ -89,6 +89,7 @@ constexpr int kDbgHostPrepass = 64; // seed thresholds with separate sampled sca
 constexpr int kDbgTimeScan = 8;  // record CUDA events around every full-shard scan launch (mips_scan_times_ms)
 constexpr int kDbgNoTma = 256;   // the producer hands over stages without loading them (power/latency split; results meaningless)
 constexpr int kDbgNoLockstep = 512;  // pairs sharing a tile sequence run free (A/B test of the L2 lock-step)
+constexpr int kDbgFourPairBlocks = 2048;  // 4 pair blocks per launch whenever > 512 queries are left (normally only for long tile sequences)
 constexpr int kDbgNoPair = 128;  // batches > 128 without tcgen05 CTA pairs (the round-1 multi-block path; A/B test)
 enum Stat { kStProdWait = 0, kStMmaWaitFull, kStMmaWaitTmem, kStEpiWaitTmem, kStEpiSelect, kStEpiCompact,
             kStNumCompact, kStNumAppend, kStTotal, kStEpiLd, kNumStats };

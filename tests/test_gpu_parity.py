@@ -576,8 +576,11 @@ def test_cta_pair_scan_matches_oracle(eng, dev, n, d, b, k, dtype):
     s, i = m.search(q, k)
     m.debug_config(32, False)
     s1, i1 = m.search(q, k)
+    m.debug_config(2048, False)                  # 4 pair blocks per launch (automatic only for very long shards)
+    s4, i4 = m.search(q, k)
     m.debug_config(0, False)
     assert torch.equal(i, i1) and torch.equal(s, s1)
+    assert torch.equal(i4, i1) and torch.equal(s4, s1)
     rs, ri = _torch_ref(e, q, k, dtype)
     exact = (q.to(dtype).double() @ e.double().T).cpu().numpy()
     rep = O.compare_topk(i.cpu().numpy(), s.cpu().numpy(), ri.cpu().numpy(), rs.cpu().numpy(), exact, rtol=1e-5, atol=1e-6)

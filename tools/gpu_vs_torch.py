@@ -10,7 +10,7 @@ for s in range(0, n, 1 << 20):
     e[s:s + c.shape[0]] = torch.nn.functional.normalize(c, dim=1).half()
 m = eng.MipsEngine(768, torch.float16, dev); m.bind(e)
 emb_dn = e.t()        # [768, n] view = the reference's operand layout (values identical)
-for b in (64, 256):
+for b in [int(x) for x in os.environ.get("DBG_BS", "64,256").split(",")]:
     q = torch.nn.functional.normalize(torch.randn(b, 768, generator=g, device=dev), dim=1)
     def ref():
         return torch.topk(torch.matmul(q.half(), emb_dn), k, dim=1)
